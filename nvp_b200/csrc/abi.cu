@@ -1,0 +1,192 @@
+// extern "C" entry points of libnvp_b200.so (see include/nvp_b200.h for the contract).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nvp {
+
+static thread_local std::string g_error;
+static thread_local int g_launches = 0;
+
+void set_error(const std::string& msg) { g_error = msg; }
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+int validate_desc(const nvp_desc* d) {
+  NVP_CHECK(d != nullptr, "nvp_desc is NULL");
+  NVP_CHECK(d->n_levels >= 1 && d->n_levels <= NVP_MAX_LEVELS, "n_levels must be in [1,32]");
+  NVP_CHECK(d->n_features == 1 || d->n_features == 2 || d->n_features == 4 || d->n_features == 8,
+            "2d n_features_per_level must be 1, 2, 4 or 8");
+  NVP_CHECK(d->sparse_features == 1 || d->sparse_features == 2 || d->sparse_features == 4 || d->sparse_features == 8,
+            "3d n_features_per_level must be 1, 2, 4 or 8");
+  NVP_CHECK(d->t_resolution >= 1 && d->x_resolution >= 1 && d->y_resolution >= 1, "3d resolutions must be >= 1");
+  NVP_CHECK(d->hidden == kHidden, "network.n_neurons must be 128");
+  NVP_CHECK(d->n_layers == 3, "network.n_hidden_layers must be 3");
+  NVP_CHECK(d->base_resolution >= 1 && d->per_level_scale > 0.0f, "bad base_resolution / per_level_scale");
+  return 0;
+}
+
+// scale_l = exp2f(l * log2f(pls)) * base - 1 ; res_l = ceil(scale_l) + 1   (tcnn grid.h semantics; the
+// resolutions equal eval.py:28-35).  fp32 steps with log2/exp2 evaluated in double and rounded once, the
+// same recipe as oracle/nvp_oracle.py::level_table so both sides agree bit-for-bit.
+int build_level_table(const nvp_desc* d, LevelTab* tab, int64_t* offsets64) {
+  if (int rc = validate_desc(d)) return rc;
+  const float log2_pls = static_cast<float>(log2(static_cast<double>(d->per_level_scale)));
+  int64_t off = 0;
+  for (int l = 0; l < d->n_levels; ++l) {
+    const float arg = static_cast<float>(l) * log2_pls;
+    const float e = static_cast<float>(exp2(static_cast<double>(arg)));
+    const float s = e * static_cast<float>(d->base_resolution) - 1.0f;
+    const int res = static_cast<int>(ceilf(s)) + 1;
+    NVP_CHECK(off + static_cast<int64_t>(res) * res < (1ll << 31), "keyframe plane has more than 2^31 cells");
+    if (tab) { tab->scale[l] = s; tab->res[l] = res; tab->offset[l] = static_cast<int32_t>(off); }
+    if (offsets64) offsets64[l] = off;
+    off += static_cast<int64_t>(res) * res;
+  }
+  if (tab) { tab->offset[d->n_levels] = static_cast<int32_t>(off); tab->n_levels = d->n_levels; }
+  if (offsets64) offsets64[d->n_levels] = off;
+  return 0;
+}
+
+static int check_device_ptr(const void* p, const char* name) {
+  NVP_CHECK(p != nullptr, std::string(name) + " is NULL");
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error(std::string(name) + ": not a CUDA pointer"); return 4; }
+  NVP_CHECK(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged,
+            std::string(name) + " must be a device pointer (there is no CPU path)");
+  return 0;
+}
+
+static int check_params(const nvp_params* p) {
+  NVP_CHECK(p != nullptr, "nvp_params is NULL");
+  int rc;
+  if ((rc = check_device_ptr(p->kf_xy, "params.kf_xy"))) return rc;
+  if ((rc = check_device_ptr(p->kf_yt, "params.kf_yt"))) return rc;
+  if ((rc = check_device_ptr(p->kf_xt, "params.kf_xt"))) return rc;
+  if ((rc = check_device_ptr(p->sparse, "params.sparse"))) return rc;
+  for (int i = 0; i < 3; ++i) {
+    if ((rc = check_device_ptr(p->siren_w[i], "params.siren_w"))) return rc;
+    if ((rc = check_device_ptr(p->siren_b[i], "params.siren_b"))) return rc;
+    if ((rc = check_device_ptr(p->mod_w[i], "params.mod_w"))) return rc;
+    if ((rc = check_device_ptr(p->mod_b[i], "params.mod_b"))) return rc;
+  }
+  if ((rc = check_device_ptr(p->last_w, "params.last_w"))) return rc;
+  if ((rc = check_device_ptr(p->last_b, "params.last_b"))) return rc;
+  return 0;
+}
+
+}  // namespace nvp
+
+using namespace nvp;
+
+extern "C" {
+
+int nvp_version(void) { return 100; }
+
+const char* nvp_last_error(void) { return g_error.c_str(); }
+
+int nvp_last_launch_count(void) { return g_launches; }
+
+int nvp_latent_dim(const nvp_desc* d) { return d ? latent_dim(d) : -1; }
+
+int nvp_level_table(const nvp_desc* d, float* scales, int32_t* res, int64_t* offsets) {
+  LevelTab tab;
+  int64_t off64[NVP_MAX_LEVELS + 1];
+  if (int rc = build_level_table(d, &tab, off64)) return rc;
+  for (int l = 0; l < d->n_levels; ++l) {
+    if (scales) scales[l] = tab.scale[l];
+    if (res) res[l] = tab.res[l];
+    if (offsets) offsets[l] = off64[l];
+  }
+  if (offsets) offsets[d->n_levels] = off64[d->n_levels];
+  return 0;
+}
+
+int nvp_workspace_bytes(const nvp_desc* d, int64_t n, int mode, int what, size_t* bytes) {
+  if (int rc = validate_desc(d)) return rc;
+  NVP_CHECK(bytes != nullptr, "bytes is NULL");
+  NVP_CHECK(what == 0 || what == 1, "what must be 0 (forward) or 1 (backward)");
+  if (mode == NVP_MODE_FP32_SIMT) *bytes = simt_workspace_bytes(d, n, what);
+  else if (mode == NVP_MODE_TC_F16) *bytes = tc_workspace_bytes(d, n, what);
+  else NVP_CHECK(false, "unknown mode");
+  return 0;
+}
+
+int nvp_encode_latent(const nvp_desc* d, const nvp_params* p, const float* coords, int64_t n, float* z, void* stream) {
+  reset_launch_count();
+  LevelTab tab;
+  if (int rc = build_level_table(d, &tab, nullptr)) return rc;
+  NVP_CHECK(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  if (int rc = check_device_ptr(coords, "coords")) return rc;
+  if (int rc = check_device_ptr(z, "z")) return rc;
+  NVP_CHECK(p && p->kf_xy && p->kf_yt && p->kf_xt && p->sparse, "grid parameter pointers are NULL");
+  return launch_grid_gather(d, tab, p, coords, n, z, latent_dim(d), nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int nvp_forward(const nvp_desc* d, const nvp_params* p, const float* coords, const float* tsteps, int64_t n,
+                float* out_rgb, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  reset_launch_count();
+  LevelTab tab;
+  if (int rc = build_level_table(d, &tab, nullptr)) return rc;
+  NVP_CHECK(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  int rc;
+  if ((rc = check_params(p))) return rc;
+  if ((rc = check_device_ptr(coords, "coords"))) return rc;
+  if ((rc = check_device_ptr(tsteps, "tsteps"))) return rc;
+  if ((rc = check_device_ptr(out_rgb, "out_rgb"))) return rc;
+  if ((rc = check_device_ptr(workspace, "workspace"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == NVP_MODE_FP32_SIMT) return simt_forward(d, tab, p, coords, tsteps, n, out_rgb, workspace, workspace_bytes, st);
+  if (mode == NVP_MODE_TC_F16) return tc_forward(d, tab, p, coords, tsteps, n, out_rgb, workspace, workspace_bytes, st);
+  NVP_CHECK(false, "unknown mode");
+}
+
+static int fwd_bwd_common(const nvp_desc* d, const nvp_params* p, const float* coords, const float* tsteps,
+                          const uint8_t* gt_u8, const float* dout, int64_t n, int64_t n_global, const nvp_grads* g,
+                          float* loss_sum, float* out_rgb, void* workspace, size_t workspace_bytes, int mode,
+                          void* stream) {
+  reset_launch_count();
+  LevelTab tab;
+  if (int rc = build_level_table(d, &tab, nullptr)) return rc;
+  NVP_CHECK(n >= 0 && n_global >= n, "need 0 <= n <= n_global");
+  NVP_CHECK(g != nullptr, "nvp_grads is NULL");
+  if (n == 0) return 0;
+  int rc;
+  if ((rc = check_params(p))) return rc;
+  if ((rc = check_device_ptr(coords, "coords"))) return rc;
+  if ((rc = check_device_ptr(tsteps, "tsteps"))) return rc;
+  if (gt_u8 && (rc = check_device_ptr(gt_u8, "gt_u8"))) return rc;
+  if (dout && (rc = check_device_ptr(dout, "dout"))) return rc;
+  if ((rc = check_device_ptr(workspace, "workspace"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == NVP_MODE_FP32_SIMT)
+    return simt_fwd_bwd(d, tab, p, coords, tsteps, gt_u8, dout, n, n_global, g, loss_sum, out_rgb, workspace,
+                        workspace_bytes, st);
+  if (mode == NVP_MODE_TC_F16)
+    return tc_fwd_bwd(d, tab, p, coords, tsteps, gt_u8, dout, n, n_global, g, loss_sum, out_rgb, workspace,
+                      workspace_bytes, st);
+  NVP_CHECK(false, "unknown mode");
+}
+
+int nvp_backward(const nvp_desc* d, const nvp_params* p, const float* coords, const float* tsteps, const float* dout,
+                 int64_t n, const nvp_grads* g, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  NVP_CHECK(dout != nullptr || n == 0, "dout is NULL");
+  return fwd_bwd_common(d, p, coords, tsteps, nullptr, dout, n, n, g, nullptr, nullptr, workspace, workspace_bytes, mode,
+                        stream);
+}
+
+int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords, const float* tsteps,
+                     const uint8_t* gt_u8, int64_t n, int64_t n_global, const nvp_grads* g, float* loss_sum,
+                     float* out_rgb, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  NVP_CHECK(gt_u8 != nullptr || n == 0, "gt_u8 is NULL");
+  NVP_CHECK(loss_sum != nullptr, "loss_sum is NULL");
+  return fwd_bwd_common(d, p, coords, tsteps, gt_u8, nullptr, n, n_global, g, loss_sum, out_rgb, workspace,
+                        workspace_bytes, mode, stream);
+}
+
+}  // extern "C"

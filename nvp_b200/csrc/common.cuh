@@ -1,0 +1,86 @@
+// Shared declarations for the NVP hot-path kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/nvp_b200.h"
+
+namespace nvp {
+
+constexpr int kHidden = 128;
+
+// Thread-local error string + launch counter behind nvp_last_error()/nvp_last_launch_count().
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+void reset_launch_count();
+
+#define NVP_CHECK(cond, msg)                                   \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      ::nvp::set_error(std::string(msg));                      \
+      return 1;                                                \
+    }                                                          \
+  } while (0)
+
+#define NVP_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::nvp::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+      return 2;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+#define NVP_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    ::nvp::count_launch();                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      ::nvp::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e));     \
+      return 3;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+// DenseGrid level layout (device-visible copy passed by value to the grid kernels).
+struct LevelTab {
+  float scale[NVP_MAX_LEVELS];
+  int32_t res[NVP_MAX_LEVELS];
+  int32_t offset[NVP_MAX_LEVELS + 1];  // in cells
+  int32_t n_levels;
+};
+
+int build_level_table(const nvp_desc* d, LevelTab* tab, int64_t* offsets64);
+int validate_desc(const nvp_desc* d);
+
+inline int latent_dim(const nvp_desc* d) { return 3 * d->n_levels * d->n_features + 9 * d->sparse_features; }
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- grid.cu ------------------------------------------------------------------------------
+// z (fp32, pitch ldz floats) and/or z16 (fp16, pitch ldz16 halfs; columns [Z, ldz16) zero-filled).
+int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+                       int64_t n, float* z, int ldz, __half* z16, int ldz16, cudaStream_t st);
+// grads += scatter of dz (fp32, pitch lddz) scaled by `scale`.
+int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
+                        const float* dz, int lddz, float scale, const nvp_grads* g, cudaStream_t st);
+
+// ---- mlp_simt.cu --------------------------------------------------------------------------
+size_t simt_workspace_bytes(const nvp_desc* d, int64_t n, int what);
+int simt_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+                 const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);
+// dout == nullptr -> loss mode (gt_u8, n_global, loss_sum used); else explicit upstream gradient.
+int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+                 const float* tsteps, const uint8_t* gt_u8, const float* dout, int64_t n, int64_t n_global,
+                 const nvp_grads* g, float* loss_sum, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// ---- mlp_tc.cu ----------------------------------------------------------------------------
+size_t tc_workspace_bytes(const nvp_desc* d, int64_t n, int what);
+int tc_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+               const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+               const float* tsteps, const uint8_t* gt_u8, const float* dout, int64_t n, int64_t n_global,
+               const nvp_grads* g, float* loss_sum, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace nvp

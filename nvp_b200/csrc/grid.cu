@@ -1,0 +1,345 @@
+// Learnable positional feature lookup: gather (forward) and scatter-add (backward).
+//
+//   keyframe planes  = tcnn DenseGrid, 2-D, L levels, bilinear   (reference: modules.py:14-23,65-67;
+//                      layout eval.py:28-35 / compression.py:72,77; arithmetic SURVEY.md A.2)
+//   sparse 3-D grid  = nearest voxel + 3x3 (x,y) neighbourhood   (reference: sparsegrid.py:43-72)
+//   latent column order: xy | yt | xt | sparse                   (reference: modules.py:69,78)
+//
+// Thread mapping: one thread per (sample, level); the L threads of one sample are adjacent lanes, so
+// every plane's L*F output floats are written as one contiguous run and the three coordinate
+// loads are warp-broadcasts.  Threads with level index < 9 also fetch one voxel of the 3x3
+// neighbourhood.  All table reads go through the read-only path as F-wide vectors; the backward
+// uses F-wide vector reductions (red.global.add.v2/v4.f32, sm_90+).
+#include "common.cuh"
+
+namespace nvp {
+namespace {
+
+template <int F>
+__device__ __forceinline__ void ld_feat(const float* __restrict__ p, float (&v)[F]) {
+  if constexpr (F == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else if constexpr (F == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (F == 8) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    float4 u = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; v[4] = u.x; v[5] = u.y; v[6] = u.z; v[7] = u.w;
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) v[f] = __ldg(p + f);
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void red_feat(float* p, const float (&v)[F]) {
+  if constexpr (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  } else if constexpr (F == 4) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  } else if constexpr (F == 8) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) atomicAdd(p + f, v[f]);
+  }
+}
+
+// pos = fma(scale, u, 0.5); cell = floor(pos); frac = pos - cell     
+__device__ __forceinline__ void pos_fract(float scale, float u, int& cell, float& frac) {
+  float pos = fmaf(scale, u, 0.5f);
+  float fl = floorf(pos);
+  cell = static_cast<int>(fl);
+  frac = pos - fl;
+}
+
+// Flat cell index without clamping, wrapped modulo the level size (the tcnn edge aliasing).
+__device__ __forceinline__ int wrap_cell(int flat, int cells) {
+  if (flat >= cells) flat -= cells;
+  if (static_cast<unsigned>(flat) >= static_cast<unsigned>(cells)) {  // inputs outside [0,1]
+    flat %= cells;
+    if (flat < 0) flat += cells;
+  }
+  return flat;
+}
+
+// nearest voxel: clamp(trunc((res-1)*c + 0.5), 0, res-1), mul and add NOT fused (sparsegrid.py:43-56)
+__device__ __forceinline__ int nearest_voxel(float c, int res) {
+  float f = __fadd_rn(__fmul_rn(static_cast<float>(res - 1), c), 0.5f);
+  int i = __float2int_rz(f);
+  return min(max(i, 0), res - 1);
+}
+
+struct GridArgs {
+  LevelTab tab;
+  const float* coords;
+  int64_t n;
+  const float* kf[3];  // xy, yt, xt (latent order)
+  const float* sparse;
+  float* gkf[3];
+  float* gsparse;
+  float* z;            // fp32 latent (gather out) / dz (scatter in)
+  int ldz;
+  __half* z16;
+  int ldz16;
+  int tres, xres, yres;
+  float scale;
+};
+
+struct SampleGeom {
+  int it, ix, iy;     // keyframe cell per axis at this level
+  float wt, wx, wy;
+};
+
+template <int F2>
+__device__ __forceinline__ void plane_gather(const float* __restrict__ tab, int off, int res, int i0, float w0,
+                                             int i1, float w1, float (&acc)[F2]) {
+  const int cells = res * res;
+  const float* base = tab + static_cast<size_t>(off) * F2;
+  const int b00 = i0 + i1 * res;
+  const int c00 = wrap_cell(b00, cells), c10 = wrap_cell(b00 + 1, cells);
+  const int c01 = wrap_cell(b00 + res, cells), c11 = wrap_cell(b00 + res + 1, cells);
+  float v00[F2], v10[F2], v01[F2], v11[F2];
+  ld_feat<F2>(base + static_cast<size_t>(c00) * F2, v00);
+  ld_feat<F2>(base + static_cast<size_t>(c10) * F2, v10);
+  ld_feat<F2>(base + static_cast<size_t>(c01) * F2, v01);
+  ld_feat<F2>(base + static_cast<size_t>(c11) * F2, v11);
+  const float a0 = 1.0f - w0, a1 = 1.0f - w1;
+  const float k00 = a0 * a1, k10 = w0 * a1, k01 = a0 * w1, k11 = w0 * w1;
+#pragma unroll
+  for (int f = 0; f < F2; ++f) {
+    float r = k00 * v00[f];
+    r = fmaf(k10, v10[f], r);
+    r = fmaf(k01, v01[f], r);
+    r = fmaf(k11, v11[f], r);
+    acc[f] = r;
+  }
+}
+
+template <int F2>
+__device__ __forceinline__ void plane_scatter(float* __restrict__ gtab, int off, int res, int i0, float w0, int i1,
+                                              float w1, const float (&d)[F2]) {
+  const int cells = res * res;
+  float* base = gtab + static_cast<size_t>(off) * F2;
+  const int b00 = i0 + i1 * res;
+  const int c00 = wrap_cell(b00, cells), c10 = wrap_cell(b00 + 1, cells);
+  const int c01 = wrap_cell(b00 + res, cells), c11 = wrap_cell(b00 + res + 1, cells);
+  const float a0 = 1.0f - w0, a1 = 1.0f - w1;
+  const float k00 = a0 * a1, k10 = w0 * a1, k01 = a0 * w1, k11 = w0 * w1;
+  float v[F2];
+#pragma unroll
+  for (int f = 0; f < F2; ++f) v[f] = k00 * d[f];
+  red_feat<F2>(base + static_cast<size_t>(c00) * F2, v);
+#pragma unroll
+  for (int f = 0; f < F2; ++f) v[f] = k10 * d[f];
+  red_feat<F2>(base + static_cast<size_t>(c10) * F2, v);
+#pragma unroll
+  for (int f = 0; f < F2; ++f) v[f] = k01 * d[f];
+  red_feat<F2>(base + static_cast<size_t>(c01) * F2, v);
+#pragma unroll
+  for (int f = 0; f < F2; ++f) v[f] = k11 * d[f];
+  red_feat<F2>(base + static_cast<size_t>(c11) * F2, v);
+}
+
+constexpr int kGridThreads = 256;
+
+template <int F2, int F3>
+__global__ void __launch_bounds__(kGridThreads) grid_gather_kernel(const GridArgs a) {
+  __shared__ float s_scale[NVP_MAX_LEVELS];
+  __shared__ int s_res[NVP_MAX_LEVELS];
+  __shared__ int s_off[NVP_MAX_LEVELS];
+  const int L = a.tab.n_levels;
+  if (threadIdx.x < L) {
+    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
+    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
+    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
+  }
+  __syncthreads();
+  const int spb = kGridThreads / L;
+  const int ls = threadIdx.x / L, l = threadIdx.x - ls * L;
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * spb + ls;
+  if (ls >= spb || s >= a.n) return;
+
+  const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
+  const float sc = s_scale[l];
+  const int res = s_res[l], off = s_off[l];
+  int it, ix, iy;
+  float wt, wx, wy;
+  pos_fract(sc, t, it, wt);
+  pos_fract(sc, x, ix, wx);
+  pos_fract(sc, y, iy, wy);
+
+  float fxy[F2], fyt[F2], fxt[F2];
+  plane_gather<F2>(a.kf[0], off, res, ix, wx, iy, wy, fxy);  // xy plane: input (x, y)   modules.py:61
+  plane_gather<F2>(a.kf[1], off, res, it, wt, iy, wy, fyt);  // yt plane: input (t, y)   modules.py:63
+  plane_gather<F2>(a.kf[2], off, res, it, wt, ix, wx, fxt);  // xt plane: input (t, x)   modules.py:62
+
+  const int pw = L * F2;  // latent columns per plane
+  if (a.z != nullptr) {
+    float* zr = a.z + s * a.ldz + l * F2;
+#pragma unroll
+    for (int f = 0; f < F2; ++f) {
+      zr[f] = fxy[f];
+      zr[pw + f] = fyt[f];
+      zr[2 * pw + f] = fxt[f];
+    }
+  }
+  if (a.z16 != nullptr) {
+    __half* zr = a.z16 + s * a.ldz16 + l * F2;
+#pragma unroll
+    for (int f = 0; f < F2; ++f) {
+      zr[f] = __float2half_rn(fxy[f]);
+      zr[pw + f] = __float2half_rn(fyt[f]);
+      zr[2 * pw + f] = __float2half_rn(fxt[f]);
+    }
+    const int zdim = 3 * pw + 9 * F3;
+    for (int c = zdim + l; c < a.ldz16; c += L) a.z16[s * a.ldz16 + c] = __float2half_rn(0.0f);
+  }
+
+  // 3x3 neighbourhood of the nearest voxel (same t slice), all weights 1.
+  const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
+  for (int v = l; v < 9; v += L) {
+    const int di = v / 3 - 1, dj = v - (v / 3) * 3 - 1;
+    const int cx = min(max(vx + di, 0), a.xres - 1), cy = min(max(vy + dj, 0), a.yres - 1);
+    const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
+    float fv[F3];
+    ld_feat<F3>(a.sparse + vox * F3, fv);
+    if (a.z != nullptr) {
+#pragma unroll
+      for (int f = 0; f < F3; ++f) a.z[s * a.ldz + 3 * pw + v * F3 + f] = fv[f];
+    }
+    if (a.z16 != nullptr) {
+#pragma unroll
+      for (int f = 0; f < F3; ++f) a.z16[s * a.ldz16 + 3 * pw + v * F3 + f] = __float2half_rn(fv[f]);
+    }
+  }
+}
+
+template <int F2, int F3>
+__global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridArgs a) {
+  __shared__ float s_scale[NVP_MAX_LEVELS];
+  __shared__ int s_res[NVP_MAX_LEVELS];
+  __shared__ int s_off[NVP_MAX_LEVELS];
+  const int L = a.tab.n_levels;
+  if (threadIdx.x < L) {
+    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
+    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
+    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
+  }
+  __syncthreads();
+  const int spb = kGridThreads / L;
+  const int ls = threadIdx.x / L, l = threadIdx.x - ls * L;
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * spb + ls;
+  if (ls >= spb || s >= a.n) return;
+
+  const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
+  const float sc = s_scale[l];
+  const int res = s_res[l], off = s_off[l];
+  int it, ix, iy;
+  float wt, wx, wy;
+  pos_fract(sc, t, it, wt);
+  pos_fract(sc, x, ix, wx);
+  pos_fract(sc, y, iy, wy);
+
+  const int pw = L * F2;
+  const float* dzr = a.z + s * a.ldz;
+  float d[F2];
+  if (a.gkf[0] != nullptr) {
+#pragma unroll
+    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + l * F2 + f) * a.scale;
+    plane_scatter<F2>(a.gkf[0], off, res, ix, wx, iy, wy, d);
+  }
+  if (a.gkf[1] != nullptr) {
+#pragma unroll
+    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + l * F2 + f) * a.scale;
+    plane_scatter<F2>(a.gkf[1], off, res, it, wt, iy, wy, d);
+  }
+  if (a.gkf[2] != nullptr) {
+#pragma unroll
+    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + l * F2 + f) * a.scale;
+    plane_scatter<F2>(a.gkf[2], off, res, it, wt, ix, wx, d);
+  }
+  if (a.gsparse != nullptr) {
+    const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
+    for (int v = l; v < 9; v += L) {
+      const int di = v / 3 - 1, dj = v - (v / 3) * 3 - 1;
+      const int cx = min(max(vx + di, 0), a.xres - 1), cy = min(max(vy + dj, 0), a.yres - 1);
+      const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
+      float dv[F3];
+#pragma unroll
+      for (int f = 0; f < F3; ++f) dv[f] = __ldg(dzr + 3 * pw + v * F3 + f) * a.scale;
+      red_feat<F3>(a.gsparse + vox * F3, dv);
+    }
+  }
+}
+
+template <int F2, int F3>
+void launch_pair(bool scatter, const GridArgs& a, int blocks, cudaStream_t st) {
+  if (scatter)
+    grid_scatter_kernel<F2, F3><<<blocks, kGridThreads, 0, st>>>(a);
+  else
+    grid_gather_kernel<F2, F3><<<blocks, kGridThreads, 0, st>>>(a);
+}
+
+template <int F2>
+int dispatch_f3(bool scatter, int f3, const GridArgs& a, int blocks, cudaStream_t st) {
+  switch (f3) {
+    case 1: launch_pair<F2, 1>(scatter, a, blocks, st); return 0;
+    case 2: launch_pair<F2, 2>(scatter, a, blocks, st); return 0;
+    case 4: launch_pair<F2, 4>(scatter, a, blocks, st); return 0;
+    case 8: launch_pair<F2, 8>(scatter, a, blocks, st); return 0;
+  }
+  return 1;
+}
+
+int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
+  const int spb = kGridThreads / a.tab.n_levels;
+  const int blocks = static_cast<int>((a.n + spb - 1) / spb);
+  if (blocks == 0) return 0;
+  int rc = 1;
+  switch (f2) {
+    case 1: rc = dispatch_f3<1>(scatter, f3, a, blocks, st); break;
+    case 2: rc = dispatch_f3<2>(scatter, f3, a, blocks, st); break;
+    case 4: rc = dispatch_f3<4>(scatter, f3, a, blocks, st); break;
+    case 8: rc = dispatch_f3<8>(scatter, f3, a, blocks, st); break;
+  }
+  NVP_CHECK(rc == 0, "n_features_per_level must be 1, 2, 4 or 8");
+  NVP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, int64_t n,
+                       float* z, int ldz, __half* z16, int ldz16, cudaStream_t st) {
+  GridArgs a{};
+  a.tab = tab;
+  a.coords = coords;
+  a.n = n;
+  a.kf[0] = p->kf_xy; a.kf[1] = p->kf_yt; a.kf[2] = p->kf_xt;
+  a.sparse = p->sparse;
+  a.z = z; a.ldz = ldz; a.z16 = z16; a.ldz16 = ldz16;
+  a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
+  a.scale = 1.0f;
+  return dispatch(false, d->n_features, d->sparse_features, a, st);
+}
+
+int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, const float* dz,
+                        int lddz, float scale, const nvp_grads* g, cudaStream_t st) {
+  if (!g->kf_xy && !g->kf_yt && !g->kf_xt && !g->sparse) return 0;
+  GridArgs a{};
+  a.tab = tab;
+  a.coords = coords;
+  a.n = n;
+  a.gkf[0] = g->kf_xy; a.gkf[1] = g->kf_yt; a.gkf[2] = g->kf_xt;
+  a.gsparse = g->sparse;
+  a.z = const_cast<float*>(dz); a.ldz = lddz;
+  a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
+  a.scale = scale;
+  return dispatch(true, d->n_features, d->sparse_features, a, st);
+}
+
+}  // namespace nvp

@@ -1,0 +1,39 @@
+"""Multi-resolution dense 2-D keyframe grid: the `tcnn.Encoding(n_input_dims=2, DenseGrid)` surface.
+
+Mirrors the operator boundary the reference uses (modules.py:14-23): ctor `(n_input_dims, encoding_config)`,
+attributes `.params` (flat fp32 nn.Parameter, level-major / cell / feature-minor, no padding — the layout
+eval.py:28-35 and compression.py:72,77 rely on), `.dtype`, `.n_output_dims`.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class Encoding(nn.Module):
+    def __init__(self, n_input_dims, encoding_config, seed=1337, dtype=torch.float32):
+        super().__init__()
+        if n_input_dims != 2 or encoding_config.get("otype", "DenseGrid") != "DenseGrid":
+            raise NotImplementedError("only the 2-D DenseGrid encoding used by NVP is built")
+        if dtype != torch.float32:
+            raise NotImplementedError("the reference fork runs fp32 parameters (modules.py:15)")
+        self.n_input_dims = 2
+        self.encoding_config = dict(encoding_config)
+        self.n_levels = encoding_config["n_levels"]
+        self.n_features = encoding_config["n_features_per_level"]
+        self.n_output_dims = self.n_levels * self.n_features
+        self.dtype = torch.float32
+        self.seed = seed
+        desc = _lib.NvpDesc(self.n_features, self.n_levels, encoding_config["base_resolution"],
+                            encoding_config["per_level_scale"], 1, 1, 1, 1, 128, 3, 30.0)
+        self.level_scales, self.level_res, self.level_offsets = _lib.level_table(desc)
+        n_params = self.level_offsets[-1] * self.n_features
+        # tcnn initialises U(-1e-4, 1e-4) from its own pcg32 (seed 1337, identical for the three planes) and
+        # does not touch torch's global RNG; a private generator keeps both properties.
+        g = torch.Generator().manual_seed(seed)
+        self.params = nn.Parameter((torch.rand(n_params, generator=g) * 2 - 1) * 1e-4)
+
+    def extra_repr(self):
+        return f"DenseGrid levels={self.n_levels} F={self.n_features} params={self.params.numel()}"

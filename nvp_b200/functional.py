@@ -1,0 +1,164 @@
+"""Autograd bridge between torch tensors and the C ABI (include/nvp_b200.h).
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic of the path
+runs in libnvp_b200.so.  There is no CPU / eager fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+# Order of the flat parameter list handed to NvpFunction (matches nvp_params field order).
+PARAM_ORDER = (
+    "kf_xy", "kf_yt", "kf_xt", "sparse",
+    "siren_w0", "siren_w1", "siren_w2", "siren_b0", "siren_b1", "siren_b2",
+    "last_w", "last_b",
+    "mod_w0", "mod_w1", "mod_w2", "mod_b0", "mod_b1", "mod_b2",
+)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pack_ptrs(ts: Sequence[Optional[torch.Tensor]]) -> _lib.NvpPtrs:
+    p = _lib.NvpPtrs()
+    p.kf_xy, p.kf_yt, p.kf_xt, p.sparse = _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3])
+    for i in range(3):
+        p.siren_w[i] = _ptr(ts[4 + i])
+        p.siren_b[i] = _ptr(ts[7 + i])
+        p.mod_w[i] = _ptr(ts[12 + i])
+        p.mod_b[i] = _ptr(ts[15 + i])
+    p.last_w, p.last_b = _ptr(ts[10]), _ptr(ts[11])
+    return p
+
+
+def _require_cuda(name: str, t: torch.Tensor, dtype) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is a CPU tensor: nvp_b200 has no CPU path (move the model and inputs to CUDA)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+class _Workspace:
+    """Grow-only per-device scratch handed to the library (the library never allocates)."""
+
+    def __init__(self):
+        self.buf: Dict[torch.device, torch.Tensor] = {}
+
+    def get(self, device, nbytes: int) -> torch.Tensor:
+        nbytes = max(int(nbytes), 256)
+        b = self.buf.get(device)
+        if b is None or b.numel() < nbytes:
+            self.buf[device] = b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return b
+
+
+WORKSPACE = _Workspace()
+_last_launches = 0
+
+
+def last_launch_count() -> int:
+    return _last_launches
+
+
+def _note_launches():
+    global _last_launches
+    _last_launches = _lib.load().nvp_last_launch_count()
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def forward(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], coords: torch.Tensor, tsteps: torch.Tensor,
+            mode: int) -> torch.Tensor:
+    coords = _require_cuda("all_coords", coords, torch.float32)
+    tsteps = _require_cuda("temporal_steps", tsteps, torch.float32)
+    params = [_require_cuda(f"parameter {PARAM_ORDER[i]}", p.detach(), torch.float32) for i, p in enumerate(params)]
+    n = coords.shape[0]
+    out = torch.empty((n, 3), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        ws = WORKSPACE.get(coords.device, _lib.workspace_bytes(desc, n, mode, 0))
+        pp = pack_ptrs(params)
+        rc = _lib.load().nvp_forward(C.byref(desc), C.byref(pp), coords.data_ptr(), tsteps.data_ptr(), n,
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), mode, _stream_ptr(coords.device))
+    _lib.check(rc, "nvp_forward")
+    _note_launches()
+    return out
+
+
+def backward(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequence[Optional[torch.Tensor]],
+             coords: torch.Tensor, tsteps: torch.Tensor, dout: torch.Tensor, mode: int) -> None:
+    """grads[i] += d(sum(dout*rgb))/d(params[i]) for every non-None grads[i]."""
+    coords = _require_cuda("all_coords", coords, torch.float32)
+    tsteps = _require_cuda("temporal_steps", tsteps, torch.float32)
+    dout = _require_cuda("grad_output", dout, torch.float32)
+    params = [_require_cuda(f"parameter {PARAM_ORDER[i]}", p.detach(), torch.float32) for i, p in enumerate(params)]
+    n = coords.shape[0]
+    with torch.cuda.device(coords.device):
+        ws = WORKSPACE.get(coords.device, _lib.workspace_bytes(desc, n, mode, 1))
+        pp, gg = pack_ptrs(params), pack_ptrs(grads)
+        rc = _lib.load().nvp_backward(C.byref(desc), C.byref(pp), coords.data_ptr(), tsteps.data_ptr(),
+                                      dout.data_ptr(), n, C.byref(gg), ws.data_ptr(), ws.numel(), mode,
+                                      _stream_ptr(coords.device))
+    _lib.check(rc, "nvp_backward")
+    _note_launches()
+
+
+def fwd_loss_bwd(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequence[Optional[torch.Tensor]],
+                 coords: torch.Tensor, tsteps: torch.Tensor, gt_u8: torch.Tensor, n_global: int,
+                 loss_sum: torch.Tensor, mode: int, out_rgb: Optional[torch.Tensor] = None) -> None:
+    """One fused step: loss_sum[0] += sum((rgb-gt)^2); grads += d(mean over 3*n_global)/d(params)."""
+    coords = _require_cuda("all_coords", coords, torch.float32)
+    tsteps = _require_cuda("temporal_steps", tsteps, torch.float32)
+    gt_u8 = _require_cuda("img", gt_u8, torch.uint8)
+    params = [_require_cuda(f"parameter {PARAM_ORDER[i]}", p.detach(), torch.float32) for i, p in enumerate(params)]
+    n = coords.shape[0]
+    with torch.cuda.device(coords.device):
+        ws = WORKSPACE.get(coords.device, _lib.workspace_bytes(desc, n, mode, 1))
+        pp, gg = pack_ptrs(params), pack_ptrs(grads)
+        rc = _lib.load().nvp_fwd_loss_bwd(C.byref(desc), C.byref(pp), coords.data_ptr(), tsteps.data_ptr(),
+                                          gt_u8.data_ptr(), n, n_global, C.byref(gg), loss_sum.data_ptr(),
+                                          _ptr(out_rgb), ws.data_ptr(), ws.numel(), mode, _stream_ptr(coords.device))
+    _lib.check(rc, "nvp_fwd_loss_bwd")
+    _note_launches()
+
+
+def encode_latent(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], coords: torch.Tensor) -> torch.Tensor:
+    coords = _require_cuda("all_coords", coords, torch.float32)
+    n = coords.shape[0]
+    zdim = _lib.load().nvp_latent_dim(C.byref(desc))
+    z = torch.empty((n, zdim), dtype=torch.float32, device=coords.device)
+    ps: List[Optional[torch.Tensor]] = [_require_cuda("grid parameter", p.detach(), torch.float32) for p in params[:4]]
+    ps += [None] * (len(PARAM_ORDER) - 4)
+    with torch.cuda.device(coords.device):
+        pp = pack_ptrs(ps)
+        rc = _lib.load().nvp_encode_latent(C.byref(desc), C.byref(pp), coords.data_ptr(), n, z.data_ptr(),
+                                           _stream_ptr(coords.device))
+    _lib.check(rc, "nvp_encode_latent")
+    _note_launches()
+    return z
+
+
+class NvpFunction(torch.autograd.Function):
+    """rgb = NVP.forward(coords, tsteps; params) with the reference's autograd contract
+    (gradients for the 18 parameter tensors, none for the inputs — SURVEY.md 3.3)."""
+
+    @staticmethod
+    def forward(ctx, desc, mode, coords, tsteps, *params):
+        ctx.desc, ctx.mode = desc, mode
+        ctx.save_for_backward(coords, tsteps, *params)
+        return forward(desc, params, coords, tsteps, mode)
+
+    @staticmethod
+    def backward(ctx, dout):
+        coords, tsteps, *params = ctx.saved_tensors
+        grads = [torch.zeros_like(p) if ctx.needs_input_grad[4 + i] else None for i, p in enumerate(params)]
+        backward(ctx.desc, params, grads, coords, tsteps, dout.reshape(-1, 3), ctx.mode)
+        return (None, None, None, None, *grads)

@@ -1,0 +1,22 @@
+"""3-D sparse positional feature grid: parameter container mirroring /root/reference/sparsegrid.py:4-21.
+
+The lookup itself (nearest voxel + 3x3 neighbourhood, sparsegrid.py:23-72) runs inside the fused CUDA
+path; this class owns `embeddings` [T,X,Y,F] and the attributes eval.py / compression.py read.
+"""
+import torch
+from torch import nn
+
+
+class SparseGrid(nn.Module):
+    def __init__(self, level_dim=2, x_resolution=300, y_resolution=300, t_resolution=600, upsample=False):
+        super().__init__()
+        if upsample:
+            raise NotImplementedError("SparseGrid(upsample=True) is disabled in both reference configs and not built")
+        self.level_dim = level_dim
+        self.x_resolution, self.y_resolution, self.t_resolution = x_resolution, y_resolution, t_resolution
+        self.embeddings = nn.Parameter(torch.empty(t_resolution, x_resolution, y_resolution, level_dim))
+        self.upsample = upsample
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embeddings.data.uniform_(-1e-4, 1e-4)  # sparsegrid.py:19-21
