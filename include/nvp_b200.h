@@ -131,6 +131,12 @@ int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords
 /* Number of kernels the last call on this thread enqueued (for bench.py's gpu_launches). */
 int nvp_last_launch_count(void);
 
+/* Hardware self-test of the tcgen05 building blocks (one 128x128 tile, fp16 operands, fp32 result D[128,128]):
+ *   mode 0: D = A[128,K] * B[128,K]^T  (K-major operands,  K in {64,128,192,256})
+ *   mode 1: D = A[K,128]^T * B[K,128]  (MN-major operands, K % 16 == 0, K <= 128)
+ * No reference counterpart; used by the GPU tests only. */
+int nvp_selftest_umma(const void* A, const void* B, float* D, int K, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

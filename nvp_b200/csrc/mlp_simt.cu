@@ -25,7 +25,8 @@ struct GemmArgs {
   const float* bias;                  // per-n bias or nullptr
   int act;                            // 0 none, 1 LeakyReLU(0.01)
   int accumulate;                     // C = epi(C + A*B)
-  int klen;                           // K range per blockIdx.z (split-K -> atomics)
+  int klen;                           // K range per blockIdx.z
+  int atomic_out;                     // C += A*B with atomics (split-K / gradient accumulation)
 };
 
 constexpr int BM = 128, BN = 128, BK = 8, GT = 256;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(const GemmArgs g) {
     __syncthreads();
   }
 
-  const bool split = gridDim.z > 1;
+  const bool split = g.atomic_out != 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + ty * 8 + i;
@@ -164,7 +165,7 @@ int linear_wgrad(const float* dY, const float* X, int ldx, int K, float* dW, int
   g.M = H; g.N = K; g.K = static_cast<int>(n);
   g.A = dY; g.sam = 1; g.sak = H;
   g.B = X; g.sbk = ldx; g.sbn = 1;
-  g.C = dW; g.ldc = lddw;
+  g.C = dW; g.ldc = lddw; g.atomic_out = 1;
   const int splits = static_cast<int>(std::max<int64_t>(2, std::min<int64_t>(592, n / 512)));
   return gemm(g, splits, st);
 }

@@ -1,0 +1,177 @@
+// Blackwell (sm_100a) primitives used by the tensor-core kernels: mbarrier, TMA bulk copies,
+// TMEM allocation, tcgen05.mma / commit / ld, UMMA shared-memory and instruction descriptors.
+// Hand-written inline PTX; descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptor".
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace nvp {
+namespace tc {
+
+// ---- operand tile format ----------------------------------------------------------------
+// Every fp16 MMA operand lives (in HBM and in shared memory alike) as "panels":
+//   panel = 128 rows x 64 halfs (128 B per row, 16 KiB), 1024-B aligned, with the 128-byte swizzle:
+//   the 16-byte chunk j of row r is stored at chunk (j ^ (r & 7)).
+// Read as  K-major  (row = M/N index, 64 contiguous K)  : SWIZZLE_128B, SBO = 1024 B.
+// Read as  MN-major (row = K index, 64 contiguous M/N)  : SWIZZLE_128B, SBO = 1024 B, LBO = panel stride.
+// Because both views share one physical layout, the same stored tile feeds the forward/dgrad GEMMs
+// (activations as K-major A) and the wgrad GEMMs (activations as MN-major A/B, samples as K).
+constexpr int kPanelRows = 128;
+constexpr int kPanelCols = 64;
+constexpr int kPanelBytes = kPanelRows * kPanelCols * 2;  // 16384
+
+// byte offset of element (r, c) inside a panel, c in [0,64)
+__host__ __device__ __forceinline__ uint32_t panel_offset(int r, int c) {
+  return static_cast<uint32_t>(r) * 128u + ((((static_cast<uint32_t>(c) >> 3) ^ (static_cast<uint32_t>(r) & 7u)) << 4)) +
+         ((static_cast<uint32_t>(c) & 7u) << 1);
+}
+// byte offset of the 16-byte chunk j (8 halfs, columns 8j..8j+7) of row r
+__host__ __device__ __forceinline__ uint32_t panel_chunk_offset(int r, int j) {
+  return static_cast<uint32_t>(r) * 128u + (((static_cast<uint32_t>(j) ^ (static_cast<uint32_t>(r) & 7u)) << 4));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- proxies / fences -----------------------------------------------------------------------
+// generic-proxy smem writes (st.shared) -> visible to the async proxy (UMMA operand reads, bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---- TMA bulk copies (1-D, no tensor map: tiles are stored pre-swizzled) ----------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the smem SOURCE of all committed bulk stores has been read (buffer reusable)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- TMEM -----------------------------------------------------------------------------------
+// One full warp executes alloc/dealloc. ncols: power of two in [32, 512].
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA descriptors -----------------------------------------------------------------------
+// Shared-memory matrix descriptor (64-bit):
+//   [0,14)  start address >> 4      [16,30) leading byte offset >> 4     [32,46) stride byte offset >> 4
+//   [46,48) version (1 on sm_100)   [49,52) base offset (0: panels are 1024-B aligned)
+//   [61,64) layout type: 0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// K-major view of a panel, K sub-block kk (16 halfs = 32 B inside the 128-B swizzle atom)
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t panel_addr, int kk) {
+  return umma_desc_sw128(panel_addr + static_cast<uint32_t>(kk) * 32u, 16u, 1024u);
+}
+// MN-major view: rows are K.  K sub-block kk = 16 rows (2048 B).  mn_panel_stride = byte distance between
+// consecutive 64-wide MN panels (LBO).  `row0` selects the starting K row (multiple of 8).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t panel_addr, int kk, uint32_t mn_panel_stride) {
+  return umma_desc_sw128(panel_addr + static_cast<uint32_t>(kk) * 2048u, mn_panel_stride, 1024u);
+}
+
+// Instruction descriptor (32-bit) for kind::f16: fp16 A/B (format 0) or bf16 (format 1), fp32 accumulate.
+//   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format  [15] A major (1 = MN)  [16] B major (1 = MN)
+//   [17,23) N >> 3            [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn, bool b_mn, bool bf16 = false) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace tc
+}  // namespace nvp
