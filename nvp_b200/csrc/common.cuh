@@ -59,9 +59,10 @@ inline int latent_dim(const nvp_desc* d) { return 3 * d->n_levels * d->n_feature
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- grid.cu ------------------------------------------------------------------------------
-// z (fp32, pitch ldz floats) and/or z16 (fp16, pitch ldz16 halfs; columns [Z, ldz16) zero-filled).
+// z (fp32 row-major, pitch ldz floats) and/or z16t (fp16 MMA tile format, kz 64-column panels per
+// 128-sample tile; see tc_common.cuh).
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
-                       int64_t n, float* z, int ldz, __half* z16, int ldz16, cudaStream_t st);
+                       int64_t n, float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st);
 // grads += scatter of dz (fp32, pitch lddz) scaled by `scale`.
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
                         const float* dz, int lddz, float scale, const nvp_grads* g, cudaStream_t st);

@@ -11,6 +11,7 @@
 // neighbourhood.  All table reads go through the read-only path as F-wide vectors; the backward
 // uses F-wide vector reductions (red.global.add.v2/v4.f32, sm_90+).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nvp {
 namespace {
@@ -83,8 +84,9 @@ struct GridArgs {
   float* gsparse;
   float* z;            // fp32 latent (gather out) / dz (scatter in)
   int ldz;
-  __half* z16;
-  int ldz16;
+  uint8_t* z16t;       // fp16 latent in MMA tile format: [tile][panel][128 rows x 64 halfs, 128B-swizzled]
+  int kz;              // panels per tile (ZP / 64)
+  int64_t n_pad;       // rows to write (multiple of 128; rows >= n are zero-filled)
   int tres, xres, yres;
   float scale;
 };
@@ -161,7 +163,19 @@ __global__ void __launch_bounds__(kGridThreads) grid_gather_kernel(const GridArg
   const int spb = kGridThreads / L;
   const int ls = threadIdx.x / L, l = threadIdx.x - ls * L;
   const int64_t s = static_cast<int64_t>(blockIdx.x) * spb + ls;
-  if (ls >= spb || s >= a.n) return;
+  if (ls >= spb) return;
+  if (s >= a.n) {
+    // padding rows of the last 128-sample tile: all-zero latent (keeps the wgrad contraction clean)
+    if (a.z16t != nullptr && s < a.n_pad) {
+      const int64_t tile = s >> 7;
+      const int r = static_cast<int>(s & 127);
+      for (int c = l * 8; c < a.kz * 64; c += L * 8) {
+        uint8_t* dst = a.z16t + (tile * a.kz + (c >> 6)) * tc::kPanelBytes + tc::panel_offset(r, c & 63);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    return;
+  }
 
   const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
   const float sc = s_scale[l];
@@ -187,16 +201,24 @@ __global__ void __launch_bounds__(kGridThreads) grid_gather_kernel(const GridArg
       zr[2 * pw + f] = fxt[f];
     }
   }
-  if (a.z16 != nullptr) {
-    __half* zr = a.z16 + s * a.ldz16 + l * F2;
+  if (a.z16t != nullptr) {
+    const int64_t tile = s >> 7;
+    const int r = static_cast<int>(s & 127);
+    uint8_t* tbase = a.z16t + tile * a.kz * tc::kPanelBytes;
+    auto put = [&](int col, const float (&v)[F2]) {
+      __half* dst = reinterpret_cast<__half*>(tbase + (col >> 6) * tc::kPanelBytes + tc::panel_offset(r, col & 63));
 #pragma unroll
-    for (int f = 0; f < F2; ++f) {
-      zr[f] = __float2half_rn(fxy[f]);
-      zr[pw + f] = __float2half_rn(fyt[f]);
-      zr[2 * pw + f] = __float2half_rn(fxt[f]);
-    }
+      for (int f = 0; f < F2; ++f) dst[f] = __float2half_rn(v[f]);
+    };
+    put(l * F2, fxy);
+    put(pw + l * F2, fyt);
+    put(2 * pw + l * F2, fxt);
+    // padding columns [Z, ZP): column Z carries the constant 1 (bias-gradient column of the wgrad GEMM;
+    // the matching forward weight columns are zero), the rest are zero.
     const int zdim = 3 * pw + 9 * F3;
-    for (int c = zdim + l; c < a.ldz16; c += L) a.z16[s * a.ldz16 + c] = __float2half_rn(0.0f);
+    for (int c = zdim + l; c < a.kz * 64; c += L)
+      *reinterpret_cast<__half*>(tbase + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63)) =
+          __float2half_rn(c == zdim ? 1.0f : 0.0f);
   }
 
   // 3x3 neighbourhood of the nearest voxel (same t slice), all weights 1.
@@ -211,9 +233,17 @@ __global__ void __launch_bounds__(kGridThreads) grid_gather_kernel(const GridArg
 #pragma unroll
       for (int f = 0; f < F3; ++f) a.z[s * a.ldz + 3 * pw + v * F3 + f] = fv[f];
     }
-    if (a.z16 != nullptr) {
+    if (a.z16t != nullptr) {
+      const int64_t tile = s >> 7;
+      const int r = static_cast<int>(s & 127);
+      const int col = 3 * pw + v * F3;
+      uint8_t* tbase = a.z16t + tile * a.kz * tc::kPanelBytes;
 #pragma unroll
-      for (int f = 0; f < F3; ++f) a.z16[s * a.ldz16 + 3 * pw + v * F3 + f] = __float2half_rn(fv[f]);
+      for (int f = 0; f < F3; ++f) {  // per element: col need not be F3-aligned when F2 != F3
+        const int c = col + f;
+        *reinterpret_cast<__half*>(tbase + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63)) =
+            __float2half_rn(fv[f]);
+      }
     }
   }
 }
@@ -297,7 +327,8 @@ int dispatch_f3(bool scatter, int f3, const GridArgs& a, int blocks, cudaStream_
 
 int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
   const int spb = kGridThreads / a.tab.n_levels;
-  const int blocks = static_cast<int>((a.n + spb - 1) / spb);
+  const int64_t rows = (!scatter && a.z16t != nullptr) ? a.n_pad : a.n;
+  const int blocks = static_cast<int>((rows + spb - 1) / spb);
   if (blocks == 0) return 0;
   int rc = 1;
   switch (f2) {
@@ -314,14 +345,14 @@ int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
 }  // namespace
 
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, int64_t n,
-                       float* z, int ldz, __half* z16, int ldz16, cudaStream_t st) {
+                       float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st) {
   GridArgs a{};
   a.tab = tab;
   a.coords = coords;
   a.n = n;
   a.kf[0] = p->kf_xy; a.kf[1] = p->kf_yt; a.kf[2] = p->kf_xt;
   a.sparse = p->sparse;
-  a.z = z; a.ldz = ldz; a.z16 = z16; a.ldz16 = ldz16;
+  a.z = z; a.ldz = ldz; a.z16t = z16t; a.kz = kz; a.n_pad = (n + 127) / 128 * 128;
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
   a.scale = 1.0f;
   return dispatch(false, d->n_features, d->sparse_features, a, st);
