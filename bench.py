@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the NVP per-coordinate hot path (BASELINE.json metric: Mpixels/s fwd+bwd @1920x1080x600).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config s|l]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1)
+
+A "step" is one pass of the hot path over one batch of N=1,245,184 sampled coordinates (dataio.py:91)
+of a synthetic 1920x1080x600 video: zero the gradient buffer, positional-feature gather, fused
+modulator+SIREN forward, L2 loss, fused backward, weight gradients, grid scatter-add and — with more
+than one GPU — one NCCL all-reduce of the flat gradient buffer.  Prints ONE JSON line (rank 0).
+
+  value      Mpixels/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public module API with HOST (pinned) inputs: H2D copies of
+             coords/tsteps/gt and the D2H read of the loss are inside the timed region
+  roofline   the dominant kernel's achieved algorithmic rate vs the measured peak (MEASURED_PEAKS.json),
+             timed live with CUDA events on the launch stream; all kernels listed under "kernels"
+  cpu_baseline  the oracle (CPU port of the reference arithmetic) timed on this box's host cores on a
+             bounded sample of the same workload
+--impl reference times that CPU port alone (the reference itself is CPU-runnable only through the
+oracle here: its sole native dependency, a tiny-cuda-nn fork, is un-vendored and the reference tree is
+not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SAMPLES = 1245184            # dataio.py:91
+VIDEO = (600, 1080, 1920)      # T, H, W
+METRIC = "Mpixels/sec fwd+bwd @1920x1080x600"
+UNIT = "Mpixels/s"
+
+
+# ------------------------------------------------------------------------------------------
+def load_config(name: str) -> dict:
+    with open(os.path.join(ROOT, "config", f"config_nvp_{name}.json")) as f:
+        return json.load(f)["nvp"]
+
+
+def synth_batch(n: int, seed: int):
+    """One sampler batch (dataio.py:104-120) over a virtual synthetic video: the pixel value is a smooth
+    pattern plus hash noise evaluated at the sampled (t,row,col) — the 3.7 GB video is never materialised."""
+    T, Hh, Ww = VIDEO
+    g = torch.Generator().manual_seed(seed)
+    t_idx = torch.randint(0, T, (n,), generator=g)
+    p_idx = torch.randint(0, Hh * Ww, (n,), generator=g)
+    row, col = p_idx // Ww, p_idx % Ww
+    coords = torch.stack((torch.linspace(0, 1, T)[t_idx], row.float() / (Hh - 1), col.float() / (Ww - 1)), dim=1)
+    half_dt = 0.5 / T
+    tsteps = torch.linspace(half_dt, 1 - half_dt, T)[t_idx]
+    x, y, t = coords[:, 2], coords[:, 1], coords[:, 0]
+    chans = []
+    for c in range(3):
+        base = 0.5 + 0.25 * torch.sin(6.2831853 * ((c + 1) * x + 0.5 * t)) * torch.cos(6.2831853 * ((c + 2) * y - 0.3 * t))
+        noise = (((p_idx * 2654435761 + t_idx * 40503 + c * 97) % 1024).float() / 1024.0 - 0.5) * 0.06
+        chans.append(((base + noise) * 255.0).clamp(0, 255).to(torch.uint8))
+    return coords.contiguous(), tsteps.contiguous(), torch.stack(chans, dim=1).contiguous()
+
+
+def attach_flat_grads(model):
+    """All gradients as views into ONE flat fp32 buffer (single memset, single NCCL all-reduce)."""
+    ps = [p for p in model.parameters() if p.requires_grad]
+    offs, total = [], 0
+    for p in ps:
+        offs.append(total)
+        total += (p.numel() + 63) // 64 * 64
+    flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+    for p, o in zip(ps, offs):
+        p.grad = flat[o:o + p.numel()].view_as(p)
+    return flat
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# Algorithmic work per pixel (every gathered/scattered element counted once, no cache credit).
+def algorithmic_work(F: int):
+    G = (3 * 16 * 4 + 9) * F * 4          # grid gather bytes / px  (1608 B for S)
+    Z = 57 * F
+    fwd_mac = Z * 128 + 2 * (128 + Z) * 128 + (128 + 2 * 128 * 128 + 384)
+    return {
+        "grid_gather": ("hbm", G + 12),                    # + coords
+        "grid_scatter": ("hbm", G + 12),
+        "mlp_forward": ("tensor", 2 * fwd_mac),
+        "mlp_backward": ("tensor", 2 * (fwd_mac - 128)),   # dgrad (none to the scalar SIREN input)
+        "mlp_wgrad": ("tensor", 2 * fwd_mac),
+        "total_bytes": 2 * G + 31, "total_flop": 3 * 2 * fwd_mac - 2 * 128,
+    }
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_port_step_time(cfg_json: dict, n_sample: int, steps: int, warmup: int, seed: int = 0):
+    """fwd + loss + bwd of the oracle (CPU restatement of the reference) on n_sample coordinates of the workload."""
+    from oracle import nvp_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.NVPConfig.from_json(cfg_json)
+    p = O.init_params(cfg, seed=seed)
+    coords, tsteps, gt = synth_batch(n_sample, seed + 1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.nvp_loss_and_grads(p, coords, tsteps, gt, cfg, n_global=N_SAMPLES)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the CPU port alone, same metric/config keys, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_json = load_config(args.config)
+    n_sample = N_SAMPLES // 4
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    t = cpu_port_step_time(cfg_json, n_sample, steps, warmup)
+    v = n_sample / t / 1e6
+    cores = os.cpu_count() or 1
+    sample = f"{n_sample} of {N_SAMPLES} coordinates per step (1/4 batch), {steps} timed steps after {warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(args, "cpu oracle port"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = pure-PyTorch CPU path restated by oracle/ (tiny-cuda-nn DenseGrid restated; see DESIGN.md)",
+    }))
+
+
+def bench_config(args, mode):
+    return {"workload": f"synthetic 1920x1080x600 (UVG Jockey stand-in), config_nvp_{args.config}, "
+                        f"{N_SAMPLES} sampled coordinates per step per GPU",
+            "nvp_config": f"config_nvp_{args.config}", "samples_per_step_per_gpu": N_SAMPLES, "mode": mode,
+            "step": "grad-buffer zero + gather + fused MLP fwd + L2 loss + fused bwd + wgrad + grid scatter"
+                    + (" + NCCL all-reduce of the flat gradient buffer" if args.gpus > 1 else ""),
+            "l2": "working set >> L2 (543 MB params + 543 MB grads + 4.6 GB activation tiles per step); 8 rotating input batches",
+            "parallelism": f"dp{args.gpus}"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import nvp_b200
+    from nvp_b200 import _lib, functional
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    cfg_json = load_config(args.config)
+    torch.manual_seed(0)
+    model = nvp_b200.NVP(type="nvp", out_features=3, encoding_config=cfg_json, mode=args.mode).to(dev)
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    flat = attach_flat_grads(model)
+    n, n_global = N_SAMPLES, N_SAMPLES * world
+    F = cfg_json["2d_encoding_xy"]["n_features_per_level"]
+
+    n_pool = 8
+    host = []
+    for i in range(n_pool):
+        c, t, g = synth_batch(n, 1000 * rank + i)
+        host.append((c.pin_memory(), t.pin_memory(), g.pin_memory()))
+    resident = [(c.to(dev), t.to(dev), g.to(dev)) for c, t, g in host]
+    stage = (torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1]), torch.empty_like(resident[0][2]))
+    loss_sum = torch.zeros(1, device=dev)
+    launches = [0]
+
+    def step(c, t, g):
+        flat.zero_()
+        loss_sum.zero_()
+        model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum)
+        launches[0] += functional.last_launch_count()
+        if world > 1:
+            dist.all_reduce(flat)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident measurement (value) with live per-kernel timing
+    for i in range(args.warmup):
+        step(*resident[i % n_pool])
+    sampler = ClockSampler(local)
+    launches[0] = 0
+    _lib.profile_enable(True)
+    sampler.start()
+    ms_total = timed(lambda i: step(*resident[i % n_pool]), args.steps)
+    kern = _lib.profile_read()
+    _lib.profile_enable(False)
+    gpu_launches = launches[0]
+    loss_last = float(loss_sum) / (3.0 * n)
+
+    # ---- end-to-end through the public API with host buffers
+    def e2e_step(i):
+        c, t, g = host[i % n_pool]
+        stage[0].copy_(c, non_blocking=True)
+        stage[1].copy_(t, non_blocking=True)
+        stage[2].copy_(g, non_blocking=True)
+        step(*stage)
+        _ = loss_sum.item()          # D2H read of the step's result
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    # keep the clock sampler fed for at least ~1.5 s of the same loop (short --steps runs give NVML no samples)
+    t_end = time.time() + max(0.0, 1.5 - (ms_total + ms_e2e) / 1e3)
+    i = 0
+    while time.time() < t_end:
+        step(*resident[i % n_pool]); i += 1
+        if i % 16 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = n_global / (ms_step * 1e-3) / 1e6
+        e2e_v = n_global / (ms_e2e / args.steps * 1e-3) / 1e6
+        peaks = measured_peaks()
+        work = algorithmic_work(F)
+        kernels = {}
+        for name, (ms, cnt) in kern.items():
+            if cnt == 0:
+                continue
+            avg = ms / cnt
+            ent = {"launches": cnt, "avg_ms": avg, "share_of_step": ms / ms_total}
+            if name in work:
+                bound, per_px = work[name]
+                per_launch = per_px * n
+                if bound == "hbm":
+                    ent.update(bound="hbm", achieved=per_launch / (avg * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+                else:
+                    ent.update(bound="tensor", achieved=per_launch / (avg * 1e-3) / 1e12, peak=peaks["tflops_sustained"], unit="TFLOP/s")
+                ent["frac"] = ent["achieved"] / ent["peak"]
+                ent["algorithmic_per_launch"] = per_launch
+            kernels[name] = ent
+        dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
+        d = kernels[dom]
+        roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                    "frac": d["frac"], "traffic": None, "peak_source": peaks["source"],
+                    "whole_step": {"hbm_frac": work["total_bytes"] * n / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "tensor_frac": work["total_flop"] * n / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]}}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.mode == "tc" else "f32",
+            "data": "synthetic", "config": bench_config(args, "tc_f16" if args.mode == "tc" else "fp32_simt"),
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": 19 * n, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "loss_last_step": loss_last,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample = N_SAMPLES // 4
+            t = cpu_port_step_time(cfg_json, n_sample, 2, 1)
+            out["cpu_baseline"] = {"value": n_sample / t / 1e6, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"{n_sample} of {N_SAMPLES} coordinates (1/4 batch), 2 timed steps after 1 warm-up; "
+                                             "oracle/ CPU port of the reference arithmetic (torch CPU, all host threads)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="s", choices=["s", "l"])
+    ap.add_argument("--mode", default="tc", choices=["tc", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,9 +131,19 @@ int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords
 /* Number of kernels the last call on this thread enqueued (for bench.py's gpu_launches). */
 int nvp_last_launch_count(void);
 
+/* Per-kernel device timing with CUDA events on the launch stream (bench.py's roofline leg).
+ * After nvp_profile_enable(1) every kernel the library enqueues on this thread is bracketed by an
+ * event pair; nvp_profile_read synchronises those events, returns per-kind totals and resets.
+ * Kinds: 0 weight pack, 1 grid gather, 2 MLP forward, 3 MLP backward (dgrad), 4 MLP wgrad,
+ *        5 grid scatter, 6 fp32-mode kernels, 7 misc.  No reference counterpart. */
+#define NVP_PROFILE_KINDS 8
+int nvp_profile_enable(int on);
+int nvp_profile_read(int max_kinds, float* total_ms, int* counts);
+
 /* Hardware self-test of the tcgen05 building blocks (one 128x128 tile, fp16 operands, fp32 result D[128,128]):
  *   mode 0: D = A[128,K] * B[128,K]^T  (K-major operands,  K in {64,128,192,256})
  *   mode 1: D = A[K,128]^T * B[K,128]  (MN-major operands, K % 16 == 0, K <= 128)
+ *   mode 2+x (x = 0..3): D[:, 0:16] = A[K,128]^T * B[K, 16x:16x+16]  (N = 16 block inside the swizzle atom)
  * No reference counterpart; used by the GPU tests only. */
 int nvp_selftest_umma(const void* A, const void* B, float* D, int K, int mode, void* stream);
 

@@ -41,7 +41,7 @@ class NvpPtrs(C.Structure):
 EXPORTS = (
     "nvp_version", "nvp_last_error", "nvp_level_table", "nvp_latent_dim", "nvp_workspace_bytes",
     "nvp_encode_latent", "nvp_forward", "nvp_backward", "nvp_fwd_loss_bwd", "nvp_last_launch_count",
-    "nvp_selftest_umma",
+    "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.nvp_forward.argtypes = [D, P, vp, vp, i64, vp, vp, C.c_size_t, i32, vp]
     lib.nvp_backward.argtypes = [D, P, vp, vp, vp, i64, P, vp, C.c_size_t, i32, vp]
     lib.nvp_fwd_loss_bwd.argtypes = [D, P, vp, vp, vp, i64, i64, P, vp, vp, vp, C.c_size_t, i32, vp]
+    lib.nvp_profile_enable.argtypes = [i32]
+    lib.nvp_profile_read.argtypes = [i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.nvp_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("nvp_last_error",):
@@ -112,3 +114,19 @@ def workspace_bytes(desc: NvpDesc, n: int, mode: int, what: int) -> int:
     out = C.c_size_t(0)
     check(load().nvp_workspace_bytes(C.byref(desc), n, mode, what, C.byref(out)), "nvp_workspace_bytes")
     return int(out.value)
+
+
+PROFILE_KINDS = ("pack", "grid_gather", "mlp_forward", "mlp_backward", "mlp_wgrad", "grid_scatter", "fp32_mode", "misc")
+
+
+def profile_enable(on: bool) -> None:
+    check(load().nvp_profile_enable(1 if on else 0), "nvp_profile_enable")
+
+
+def profile_read():
+    """-> {kind: (total_ms, launches)} since the last read; synchronises the recorded events."""
+    n = len(PROFILE_KINDS)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    check(load().nvp_profile_read(n, ms, cnt), "nvp_profile_read")
+    return {PROFILE_KINDS[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -2,6 +2,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -9,6 +10,30 @@ namespace nvp {
 
 static thread_local std::string g_error;
 static thread_local int g_launches = 0;
+
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> ids;      // kernel id of record i; events 2i, 2i+1
+  size_t used = 0;
+};
+static thread_local Profiler g_prof;
+
+void prof_start(int id, cudaStream_t st) {
+  if (!g_prof.on) return;
+  while (g_prof.pool.size() < g_prof.used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { g_prof.on = false; return; }
+    g_prof.pool.push_back(e);
+  }
+  g_prof.ids.push_back(id);
+  cudaEventRecord(g_prof.pool[g_prof.used], st);
+}
+void prof_stop(cudaStream_t st) {
+  if (!g_prof.on || g_prof.ids.size() * 2 != g_prof.used + 2) return;
+  cudaEventRecord(g_prof.pool[g_prof.used + 1], st);
+  g_prof.used += 2;
+}
 
 void set_error(const std::string& msg) { g_error = msg; }
 void count_launch(int n) { g_launches += n; }
@@ -91,6 +116,28 @@ const char* nvp_last_error(void) { return g_error.c_str(); }
 int nvp_last_launch_count(void) { return g_launches; }
 
 int nvp_latent_dim(const nvp_desc* d) { return d ? latent_dim(d) : -1; }
+
+int nvp_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.ids.clear();
+  return 0;
+}
+
+int nvp_profile_read(int max_kinds, float* total_ms, int* counts) {
+  NVP_CHECK(total_ms != nullptr && counts != nullptr, "total_ms / counts is NULL");
+  for (int k = 0; k < max_kinds; ++k) { total_ms[k] = 0.f; counts[k] = 0; }
+  for (size_t i = 0; i < g_prof.used / 2; ++i) {
+    NVP_CUDA(cudaEventSynchronize(g_prof.pool[2 * i + 1]));
+    float ms = 0.f;
+    NVP_CUDA(cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]));
+    const int id = g_prof.ids[i];
+    if (id >= 0 && id < max_kinds) { total_ms[id] += ms; counts[id] += 1; }
+  }
+  g_prof.used = 0;
+  g_prof.ids.clear();
+  return 0;
+}
 
 int nvp_level_table(const nvp_desc* d, float* scales, int32_t* res, int64_t* offsets) {
   LevelTab tab;

@@ -44,6 +44,16 @@ void reset_launch_count();
     }                                                                                       \
   } while (0)
 
+// Optional per-kernel CUDA-event timing (nvp_profile_enable / nvp_profile_read in the C ABI).
+enum KernelId { K_PACK = 0, K_GATHER, K_MLP_FWD, K_MLP_BWD, K_MLP_WGRAD, K_SCATTER, K_SIMT, K_MISC, K_COUNT };
+void prof_start(int id, cudaStream_t st);
+void prof_stop(cudaStream_t st);
+struct ScopedKernelTimer {
+  cudaStream_t st;
+  ScopedKernelTimer(int id, cudaStream_t s) : st(s) { prof_start(id, s); }
+  ~ScopedKernelTimer() { prof_stop(st); }
+};
+
 // DenseGrid level layout (device-visible copy passed by value to the grid kernels).
 struct LevelTab {
   float scale[NVP_MAX_LEVELS];
@@ -63,9 +73,10 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // 128-sample tile; see tc_common.cuh).
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
                        int64_t n, float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st);
-// grads += scatter of dz (fp32, pitch lddz) scaled by `scale`.
+// grads += scatter of dz (fp32, pitch lddz) scaled by `scale` (times *scale_ptr when given).
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
-                        const float* dz, int lddz, float scale, const nvp_grads* g, cudaStream_t st);
+                        const float* dz, int lddz, float scale, const float* scale_ptr, const nvp_grads* g,
+                        cudaStream_t st);
 
 // ---- mlp_simt.cu --------------------------------------------------------------------------
 size_t simt_workspace_bytes(const nvp_desc* d, int64_t n, int what);

@@ -89,6 +89,7 @@ struct GridArgs {
   int64_t n_pad;       // rows to write (multiple of 128; rows >= n are zero-filled)
   int tres, xres, yres;
   float scale;
+  const float* scale_ptr;  // optional device scalar multiplied into scale
 };
 
 struct SampleGeom {
@@ -276,20 +277,21 @@ __global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridAr
 
   const int pw = L * F2;
   const float* dzr = a.z + s * a.ldz;
+  const float scale = a.scale_ptr ? a.scale * __ldg(a.scale_ptr) : a.scale;
   float d[F2];
   if (a.gkf[0] != nullptr) {
 #pragma unroll
-    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + l * F2 + f) * a.scale;
+    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + l * F2 + f) * scale;
     plane_scatter<F2>(a.gkf[0], off, res, ix, wx, iy, wy, d);
   }
   if (a.gkf[1] != nullptr) {
 #pragma unroll
-    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + l * F2 + f) * a.scale;
+    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + l * F2 + f) * scale;
     plane_scatter<F2>(a.gkf[1], off, res, it, wt, iy, wy, d);
   }
   if (a.gkf[2] != nullptr) {
 #pragma unroll
-    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + l * F2 + f) * a.scale;
+    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + l * F2 + f) * scale;
     plane_scatter<F2>(a.gkf[2], off, res, it, wt, ix, wx, d);
   }
   if (a.gsparse != nullptr) {
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridAr
       const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
       float dv[F3];
 #pragma unroll
-      for (int f = 0; f < F3; ++f) dv[f] = __ldg(dzr + 3 * pw + v * F3 + f) * a.scale;
+      for (int f = 0; f < F3; ++f) dv[f] = __ldg(dzr + 3 * pw + v * F3 + f) * scale;
       red_feat<F3>(a.gsparse + vox * F3, dv);
     }
   }
@@ -331,6 +333,7 @@ int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
   const int blocks = static_cast<int>((rows + spb - 1) / spb);
   if (blocks == 0) return 0;
   int rc = 1;
+  ScopedKernelTimer timer(scatter ? K_SCATTER : K_GATHER, st);
   switch (f2) {
     case 1: rc = dispatch_f3<1>(scatter, f3, a, blocks, st); break;
     case 2: rc = dispatch_f3<2>(scatter, f3, a, blocks, st); break;
@@ -359,7 +362,7 @@ int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params*
 }
 
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, const float* dz,
-                        int lddz, float scale, const nvp_grads* g, cudaStream_t st) {
+                        int lddz, float scale, const float* scale_ptr, const nvp_grads* g, cudaStream_t st) {
   if (!g->kf_xy && !g->kf_yt && !g->kf_xt && !g->sparse) return 0;
   GridArgs a{};
   a.tab = tab;
@@ -370,6 +373,7 @@ int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coo
   a.z = const_cast<float*>(dz); a.ldz = lddz;
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
   a.scale = scale;
+  a.scale_ptr = scale_ptr;
   return dispatch(true, d->n_features, d->sparse_features, a, st);
 }
 

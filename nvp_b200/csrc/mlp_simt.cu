@@ -130,6 +130,7 @@ int gemm(const GemmArgs& g, int splits, cudaStream_t st) {
   splits = (g.K + a.klen - 1) / a.klen;
   dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
   const bool am = (g.sam == 1 && g.sak != 1), bn = (g.sbn == 1);
+  ScopedKernelTimer timer(K_SIMT, st);
   if (am && bn) sgemm_kernel<true, true><<<grid, GT, 0, st>>>(a);
   else if (am && !bn) sgemm_kernel<true, false><<<grid, GT, 0, st>>>(a);
   else if (!am && bn) sgemm_kernel<false, true><<<grid, GT, 0, st>>>(a);
@@ -418,7 +419,7 @@ int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, co
     NVP_LAUNCH_CHECK();
     if ((rc = linear_wgrad(w.dM, w.z, w.ldz, Z, g->mod_w[0], Z, m, st))) return rc;
     if ((rc = linear_dgrad(w.dM, p->mod_w[0], Z, Z, 1, w.dZ, w.ldz, m, st))) return rc;
-    if ((rc = launch_grid_scatter(d, tab, coords + 3 * s0, m, w.dZ, w.ldz, 1.0f, g, st))) return rc;
+    if ((rc = launch_grid_scatter(d, tab, coords + 3 * s0, m, w.dZ, w.ldz, 1.0f, nullptr, g, st))) return rc;
   }
   return 0;
 }

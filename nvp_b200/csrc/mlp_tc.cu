@@ -84,8 +84,13 @@ void add_panel(PackArgs& a, const float* src, int ld, int transpose, int r0, int
   off += static_cast<uint32_t>(rows) * 128u;
 }
 
+struct BwdArgs;
+int pack_backward_panels(const nvp_desc* d, const nvp_params* p, PackArgs& a, uint32_t base_off, BwdArgs* b);
+
 // Forward stream: [W0z] | [W1h][W1z][Ws1] | [W2h][W2z][Ws2], each as 64-wide K panels of a [128 out x K] matrix.
-int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, cudaStream_t st) {
+// When `b` is given the backward stream is packed by the same launch into `bwd_dst`.
+int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, BwdArgs* b, cudaStream_t st,
+                         uint8_t* bwd_dst = nullptr) {
   const Dims m = make_dims(d);
   PackArgs a{};
   a.dst = dst;
@@ -96,6 +101,8 @@ int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, c
     for (int q = 0; q < m.KZ; ++q) add_panel(a, p->mod_w[i], H + m.Z, 0, 0, H + 64 * q, H, m.Z - 64 * q, H, off);
     for (int q = 0; q < 2; ++q) add_panel(a, p->siren_w[i], H, 0, 0, 64 * q, H, 64, H, off);
   }
+  if (b != nullptr) pack_backward_panels(d, p, a, static_cast<uint32_t>(bwd_dst - dst), b);
+  ScopedKernelTimer timer(K_PACK, st);
   pack_weights_kernel<<<a.n, 256, 0, st>>>(a);
   NVP_LAUNCH_CHECK();
   return 0;
@@ -350,11 +357,553 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+// ==========================================================================================
+// Backward (dgrad) kernel
+// ==========================================================================================
+// Per 128-sample tile, with every gradient pre-multiplied by the power-of-two loss scale gs so that fp16
+// operands stay in range:
+//   P2  drgb = gs * dL/drgb ; da2 = drgb Wl ; dsp2 = da2*h2*cos2 ; dm2 = da2*sin2*lrelu'(h2)
+//   S2  da1 = dsp2 Ws2 ; dh1 = dm2 W2h ; dz  = dm2 W2z         (tcgen05, accumulators in TMEM)
+//   P1  dsp1 = da1*h1*cos1 ; dm1 = (dh1 + da1*sin1)*lrelu'(h1)
+//   S1  da0 = dsp1 Ws1 ; dh0 = dm1 W1h ; dz += dm1 W1z
+//   P0  dsp0 = da0*h0*cos0*w0 ; dm0 = (dh0 + da0*sin0)*lrelu'(h0)
+//   S0  dz += dm0 W0z
+//   PZ  dz -> HBM (fp32, still scaled by gs; the grid scatter un-scales)
+// The pre-activation gradient tiles dm0..2, dsp1..2 go to HBM in the MMA tile format for the wgrad
+// kernel.  The small reductions over samples (dWl, db_siren, dw/db of SIREN layer 0) are "skinny"
+// MN-major MMAs  acc[128 features, 16] += X^T R  against a per-row panel R = [drgb | 1 | 1 | 1,tau]
+// whose 16-column blocks select the output column, accumulated across tiles in one persistent TMEM
+// accumulator and flushed once per CTA.
+enum { DP_M0 = 0, DP_M1, DP_M2, DP_S1, DP_S2, DP_COUNT };
+constexpr int kBwdPanels = 14;
+
+struct BwdArgs {
+  const uint8_t* wpk;
+  uint32_t poff[kBwdPanels], pbytes[kBwdPanels];
+  const uint8_t* stash;
+  const float* tau;
+  const float* rgb;
+  const uint8_t* gt;
+  const float* dout;
+  const float* gscale;   // device: [0] gs, [1] 1/gs, [2] gs*2/(3*n_global)
+  const float* siren_w0;
+  const float* siren_b0;
+  const float* last_w;
+  float w0;
+  uint8_t* dpre;         // [tile][DP_COUNT][2 panels]
+  float* dz;             // [n_tiles*128][ZP]
+  float* loss_sum;
+  float* g_last_w; float* g_last_b; float* g_siren_b1; float* g_siren_b2; float* g_siren_w0; float* g_siren_b0;
+  int64_t n;
+  int n_tiles, ZP, nstage;
+  uint32_t stage_bytes;
+};
+
+struct BwdSmem { uint32_t sp, m, x, rp, ring, consts, bars, total; };
+__host__ __device__ inline BwdSmem bwd_smem_layout(int nstage, uint32_t stage_bytes) {
+  BwdSmem s;
+  uint32_t o = 0;
+  s.sp = o; o += 2 * kPanelBytes;
+  s.m = o; o += 2 * kPanelBytes;
+  s.x = o; o += 2 * kPanelBytes;
+  s.rp = o; o += kPanelBytes;
+  s.ring = o; o += nstage * stage_bytes;
+  s.consts = o; o += 5 * H * 4;   // ws0[H] bs0[H] wl[3][H]
+  s.bars = o; o += 64 * 8;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ void load_row32(const uint8_t* panel, int r, int c0, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(panel + panel_chunk_offset(r, (c0 >> 3) + j));
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h[k]);
+      v[8 * j + 2 * k] = f.x;
+      v[8 * j + 2 * k + 1] = f.y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const BwdSmem L = bwd_smem_layout(a.nstage, a.stage_bytes);
+  uint8_t* spbuf = smem + L.sp;
+  uint8_t* mbuf = smem + L.m;
+  uint8_t* xbuf = smem + L.x;
+  uint8_t* rp = smem + L.rp;
+  uint8_t* ring = smem + L.ring;
+  float* s_ws0 = reinterpret_cast<float*>(smem + L.consts);
+  float* s_bs0 = s_ws0 + H;
+  float* s_wl = s_ws0 + 2 * H;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* wfull = bars;
+  uint64_t* wempty = bars + 16;
+  uint64_t* acc_full = bars + 34;
+  uint64_t* epi_done = bars + 35;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < H; i += kThreads) { s_ws0[i] = __ldg(a.siren_w0 + i); s_bs0[i] = __ldg(a.siren_b0 + i); }
+  for (int i = tid; i < 3 * H; i += kThreads) s_wl[i] = __ldg(a.last_w + i);
+  if (tid == 0) {
+    for (int i = 0; i < a.nstage; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    mbar_init(acc_full, 1); mbar_init(epi_done, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t acc_da = tmem, acc_dh = tmem + 128, acc_dz = tmem + 256, acc_sk = tmem + 256 + a.ZP;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int i = 0; i < kBwdPanels; ++i, ++g) {
+          const uint32_t st = g % a.nstage, ph = (g / a.nstage) & 1;
+          mbar_wait(&wempty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&wfull[st], a.pbytes[i]);
+          bulk_g2s(ring + st * a.stage_bytes, a.wpk + a.poff[i], a.pbytes[i], &wfull[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_h = umma_idesc_f16(kTile, H, false, false);
+      const uint32_t idesc_z = umma_idesc_f16(kTile, a.ZP, false, false);
+      const uint32_t idesc_sk = umma_idesc_f16(H, 16, true, true);
+      uint32_t g = 0, n_epi = 0;
+      bool sk_started = false;
+      auto panel_gemm = [&](uint8_t* abuf_, uint32_t acc, uint32_t idesc, bool accumulate) {
+        for (int q = 0; q < 2; ++q, ++g) {
+          const uint32_t st = g % a.nstage, ph = (g / a.nstage) & 1;
+          mbar_wait(&wfull[st], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(abuf_ + q * kPanelBytes), b_addr = smem_u32(ring + st * a.stage_bytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_f16_ss(acc, umma_desc_kmajor(a_addr, kk), umma_desc_kmajor(b_addr, kk), idesc, accumulate ? 1u : 0u);
+            accumulate = true;
+          }
+          umma_commit(&wempty[st]);
+        }
+      };
+      auto skinny = [&](uint8_t* xb, int block) {
+        const uint32_t a_addr = smem_u32(xb), b_addr = smem_u32(rp) + static_cast<uint32_t>(block) * 32u;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          umma_f16_ss(acc_sk, umma_desc_mnmajor(a_addr, kk, kPanelBytes), umma_desc_mnmajor(b_addr, kk, kPanelBytes),
+                      idesc_sk, sk_started ? 1u : 0u);
+          sk_started = true;
+        }
+      };
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        // ---- step 2
+        mbar_wait(epi_done, n_epi & 1); ++n_epi;
+        tcgen05_fence_after();
+        panel_gemm(spbuf, acc_da, idesc_h, false);
+        panel_gemm(mbuf, acc_dh, idesc_h, false);
+        panel_gemm(mbuf, acc_dz, idesc_z, false);
+        skinny(xbuf, 0);
+        skinny(spbuf, 1);
+        umma_commit(acc_full);
+        // ---- step 1
+        mbar_wait(epi_done, n_epi & 1); ++n_epi;
+        tcgen05_fence_after();
+        panel_gemm(spbuf, acc_da, idesc_h, false);
+        panel_gemm(mbuf, acc_dh, idesc_h, false);
+        panel_gemm(mbuf, acc_dz, idesc_z, true);
+        skinny(spbuf, 2);
+        umma_commit(acc_full);
+        // ---- step 0
+        mbar_wait(epi_done, n_epi & 1); ++n_epi;
+        tcgen05_fence_after();
+        panel_gemm(mbuf, acc_dz, idesc_z, true);
+        skinny(spbuf, 3);
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const float gs = __ldg(a.gscale), inv_gs = __ldg(a.gscale + 1), loss_mult = __ldg(a.gscale + 2);
+    uint32_t n_acc = 0;
+    float loss_acc = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    bool any = false;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      any = true;
+      const int64_t s = static_cast<int64_t>(tile) * kTile + r;
+      const bool valid = s < a.n;
+      const float tau = valid ? __ldg(a.tau + s) : 0.0f;
+      const uint8_t* st_base = a.stash + (static_cast<size_t>(tile) * SL_COUNT) * 2 * kPanelBytes;
+      uint8_t* dp_base = a.dpre + (static_cast<size_t>(tile) * DP_COUNT) * 2 * kPanelBytes;
+      auto stash_ptr = [&](int slot) { return st_base + (static_cast<size_t>(slot) * 2 + half) * kPanelBytes; };
+      auto dpre_ptr = [&](int slot) { return dp_base + (static_cast<size_t>(slot) * 2 + half) * kPanelBytes; };
+      uint8_t* sp_panel = spbuf + half * kPanelBytes;
+      uint8_t* m_panel = mbuf + half * kPanelBytes;
+      uint8_t* x_panel = xbuf + half * kPanelBytes;
+
+      // ---------------- P2 ----------------
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      if (valid) {
+        if (a.dout != nullptr) {
+          d0 = __ldg(a.dout + s * 3) * gs; d1 = __ldg(a.dout + s * 3 + 1) * gs; d2 = __ldg(a.dout + s * 3 + 2) * gs;
+        } else {
+          const float e0 = a.rgb[s * 3] - (static_cast<float>(a.gt[s * 3]) - 127.5f) / 127.5f;
+          const float e1 = a.rgb[s * 3 + 1] - (static_cast<float>(a.gt[s * 3 + 1]) - 127.5f) / 127.5f;
+          const float e2 = a.rgb[s * 3 + 2] - (static_cast<float>(a.gt[s * 3 + 2]) - 127.5f) / 127.5f;
+          if (half == 0) loss_acc += e0 * e0 + e1 * e1 + e2 * e2;
+          d0 = e0 * loss_mult; d1 = e1 * loss_mult; d2 = e2 * loss_mult;
+        }
+      }
+      if (half == 0) {
+        b0 += d0; b1 += d1; b2 += d2;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 0)) = make_uint4(pack_half2(d0, d1), pack_half2(d2, 0.f), 0u, 0u);
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 1)) = zero;
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 2)) = make_uint4(0u, pack_half2(0.f, 1.f), 0u, 0u);
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 3)) = zero;
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 4)) = make_uint4(0u, 0u, pack_half2(1.f, 0.f), 0u);
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 5)) = zero;
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 6)) = make_uint4(0u, 0u, pack_half2(0.f, 1.f), pack_half2(tau, 0.f));
+        *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 7)) = zero;
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int pc = cc * 32, col = half * 64 + pc;
+        float hv[32], sv[32], cv[32], o[32];
+        load_row32(stash_ptr(SL_H2), r, pc, hv);
+        load_row32(stash_ptr(SL_S2), r, pc, sv);
+        load_row32(stash_ptr(SL_C2), r, pc, cv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = sv[i] * hv[i];
+        store_row32(x_panel, r, pc, o);
+        float da[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) da[i] = d0 * s_wl[col + i] + d1 * s_wl[H + col + i] + d2 * s_wl[2 * H + col + i];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = da[i] * hv[i] * cv[i];
+        store_row32(sp_panel, r, pc, o);
+        store_row32(dpre_ptr(DP_S2), r, pc, o);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = da[i] * sv[i] * (hv[i] > 0.f ? 1.f : 0.01f);
+        store_row32(m_panel, r, pc, o);
+        store_row32(dpre_ptr(DP_M2), r, pc, o);
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+
+      // ---------------- P1, P0 ----------------
+#pragma unroll 1
+      for (int layer = 1; layer >= 0; --layer) {
+        mbar_wait(acc_full, n_acc & 1); ++n_acc;
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int pc = cc * 32, col = half * 64 + pc;
+          uint32_t va[32], vh[32];
+          tmem_ld32(acc_da + lane_base + col, va);
+          tmem_ld32(acc_dh + lane_base + col, vh);
+          float hv[32], sv[32], cv[32], o[32];
+          load_row32(stash_ptr(layer == 1 ? SL_H1 : SL_H0), r, pc, hv);
+          float post = 1.0f;
+          if (layer == 1) {
+            load_row32(stash_ptr(SL_S1), r, pc, sv);
+            load_row32(stash_ptr(SL_C1), r, pc, cv);
+          } else {
+            post = a.w0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) fast_sincos(a.w0 * fmaf(tau, s_ws0[col + i], s_bs0[col + i]), sv[i], cv[i]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(va[i]) * hv[i] * cv[i] * post;
+          store_row32(sp_panel, r, pc, o);
+          if (layer == 1) store_row32(dpre_ptr(DP_S1), r, pc, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            o[i] = (__uint_as_float(vh[i]) + __uint_as_float(va[i]) * sv[i]) * (hv[i] > 0.f ? 1.f : 0.01f);
+          store_row32(m_panel, r, pc, o);
+          store_row32(dpre_ptr(layer == 1 ? DP_M1 : DP_M0), r, pc, o);
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(epi_done);
+      }
+
+      // ---------------- PZ ----------------
+      mbar_wait(acc_full, n_acc & 1); ++n_acc;
+      tcgen05_fence_after();
+      const int zh = a.ZP >> 1;
+      for (int c0 = 0; c0 < zh; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(acc_dz + lane_base + half * zh + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(a.dz + s * a.ZP + half * zh + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tcgen05_fence_before();
+    }
+    // ---------------- flush of the per-CTA reductions ----------------
+    if (any && half == 0) {
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(acc_sk + lane_base, v);
+      tmem_ld_wait();
+      const int j = r;  // feature index
+      if (a.g_last_w) {
+        atomicAdd(a.g_last_w + j, __uint_as_float(v[0]) * inv_gs);
+        atomicAdd(a.g_last_w + H + j, __uint_as_float(v[1]) * inv_gs);
+        atomicAdd(a.g_last_w + 2 * H + j, __uint_as_float(v[2]) * inv_gs);
+      }
+      if (a.g_siren_b2) atomicAdd(a.g_siren_b2 + j, __uint_as_float(v[3]) * inv_gs);
+      if (a.g_siren_b1) atomicAdd(a.g_siren_b1 + j, __uint_as_float(v[4]) * inv_gs);
+      if (a.g_siren_b0) atomicAdd(a.g_siren_b0 + j, __uint_as_float(v[5]) * inv_gs);
+      if (a.g_siren_w0) atomicAdd(a.g_siren_w0 + j, __uint_as_float(v[6]) * inv_gs);
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o2);
+        b0 += __shfl_xor_sync(0xffffffffu, b0, o2);
+        b1 += __shfl_xor_sync(0xffffffffu, b1, o2);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, o2);
+      }
+      if (lane == 0) {
+        if (a.loss_sum && a.dout == nullptr) atomicAdd(a.loss_sum, loss_acc);
+        if (a.g_last_b) {
+          atomicAdd(a.g_last_b, b0 * inv_gs); atomicAdd(a.g_last_b + 1, b1 * inv_gs); atomicAdd(a.g_last_b + 2, b2 * inv_gs);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ==========================================================================================
+// Weight-gradient kernel: dW[out, in] = sum over samples of dpre[s, out] * act[s, in]
+// ==========================================================================================
+// Both operands are MN-major views of stored tiles (K = samples).  The accumulators of all seven
+// products do not fit one SM's TMEM (512 columns), so CTAs come in two kinds, each persistent over
+// all half-tiles (64 samples per pipeline stage) with its products resident in TMEM:
+//   kind A: dW1h = dm1^T h0 | dW1z = dm1^T z | dWs1 = dsp1^T a0
+//   kind B: dW0z = dm0^T z  | dW2h = dm2^T h1 | dW2z = dm2^T z | dWs2 = dsp2^T a1
+// Column Z of every z product is the sum of dm over samples (z carries a constant-1 column) = the
+// modulator bias gradient.  Accumulators are flushed once per CTA with fp32 atomics, un-scaled by 1/gs.
+constexpr int kWgThreads = 192;
+constexpr int kHalfPanelBytes = kPanelBytes / 2;  // 64 rows
+
+struct WgArgs {
+  const uint8_t* dpre;
+  const uint8_t* stash;
+  const uint8_t* z16t;
+  const float* gscale;
+  float* g_mod_w[3];
+  float* g_mod_b[3];
+  float* g_siren_w[3];
+  int n_units;   // half tiles
+  int KZ, Z, ZP;
+  int n_a;       // CTAs [0, n_a) are kind A
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[2], empty[2], done;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool kindA = static_cast<int>(blockIdx.x) < a.n_a;
+  const int rank = kindA ? blockIdx.x : blockIdx.x - a.n_a;
+  const int stride = kindA ? a.n_a : static_cast<int>(gridDim.x) - a.n_a;
+  // operand slots inside a stage (in half-panels of 8 KiB):
+  //   kind A: dm1[2] dsp1[2] h0[2] a0[2] z[KZ]        kind B: dm0[2] dm2[2] dsp2[2] h1[2] a1[2] z[KZ]
+  const int n_half_panels = (kindA ? 8 : 10) + a.KZ;
+  const uint32_t stage_bytes = static_cast<uint32_t>(n_half_panels) * kHalfPanelBytes;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1); mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int my_units = rank < a.n_units ? (a.n_units - rank + stride - 1) / stride : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int u = rank; u < a.n_units; u += stride, ++it) {
+        const int st = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], stage_bytes);
+        uint8_t* dst = smem + st * stage_bytes;
+        const int tile = u >> 1;
+        const uint32_t hoff = static_cast<uint32_t>(u & 1) * kHalfPanelBytes;  // rows 0-63 or 64-127 of each panel
+        const uint8_t* dp = a.dpre + static_cast<size_t>(tile) * DP_COUNT * 2 * kPanelBytes;
+        const uint8_t* sb = a.stash + static_cast<size_t>(tile) * SL_COUNT * 2 * kPanelBytes;
+        const uint8_t* zt = a.z16t + static_cast<size_t>(tile) * a.KZ * kPanelBytes;
+        auto two = [&](const uint8_t* base, int slot) {
+          for (int q = 0; q < 2; ++q) {
+            bulk_g2s(dst, base + (static_cast<size_t>(slot) * 2 + q) * kPanelBytes + hoff, kHalfPanelBytes, &full[st]);
+            dst += kHalfPanelBytes;
+          }
+        };
+        if (kindA) { two(dp, DP_M1); two(dp, DP_S1); two(sb, SL_H0); two(sb, SL_A0); }
+        else { two(dp, DP_M0); two(dp, DP_M2); two(dp, DP_S2); two(sb, SL_H1); two(sb, SL_A1); }
+        for (int q = 0; q < a.KZ; ++q) {
+          bulk_g2s(dst, zt + static_cast<size_t>(q) * kPanelBytes + hoff, kHalfPanelBytes, &full[st]);
+          dst += kHalfPanelBytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_h = umma_idesc_f16(H, H, true, true);
+      const uint32_t idesc_z = umma_idesc_f16(H, a.ZP, true, true);
+      int it = 0;
+      for (int u = rank; u < a.n_units; u += stride, ++it) {
+        const int st = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(&full[st], ph);
+        tcgen05_fence_after();
+        const uint32_t sb = smem_u32(smem + st * stage_bytes);
+        auto hp = [&](int i) { return sb + static_cast<uint32_t>(i) * kHalfPanelBytes; };
+        auto prod = [&](uint32_t acc, int a_slot, int b_slot, uint32_t idesc) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_ss(acc, umma_desc_mnmajor(hp(a_slot), kk, kHalfPanelBytes), umma_desc_mnmajor(hp(b_slot), kk, kHalfPanelBytes),
+                        idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        };
+        if (kindA) {
+          prod(tmem + 0, 0, 4, idesc_h);            // dW1h = dm1^T h0
+          prod(tmem + 128, 0, 8, idesc_z);          // dW1z = dm1^T z
+          prod(tmem + 128 + a.ZP, 2, 6, idesc_h);   // dWs1 = dsp1^T a0
+        } else {
+          prod(tmem + 0, 0, 10, idesc_z);                   // dW0z = dm0^T z
+          prod(tmem + a.ZP, 2, 6, idesc_h);                 // dW2h = dm2^T h1
+          prod(tmem + a.ZP + 128, 2, 10, idesc_z);          // dW2z = dm2^T z
+          prod(tmem + 2 * a.ZP + 128, 4, 8, idesc_h);       // dWs2 = dsp2^T a1
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(&done);
+    }
+  } else if (my_units > 0) {
+    // flush warps (4): thread = output feature row
+    mbar_wait(&done, 0);
+    tcgen05_fence_after();
+    const int quarter = warp & 3;
+    const int j = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const float inv_gs = __ldg(a.gscale + 1);
+    auto flush_h = [&](uint32_t acc, float* g, int ld, int col_off) {
+      if (g == nullptr) return;
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(acc + lane_base + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(g + static_cast<size_t>(j) * ld + col_off + c0 + i, __uint_as_float(v[i]) * inv_gs);
+      }
+    };
+    auto flush_z = [&](uint32_t acc, float* gw, int ld, int col_off, float* gb) {
+      for (int c0 = 0; c0 < a.ZP; c0 += 32) {
+        if (c0 > a.Z) break;
+        uint32_t v[32];
+        tmem_ld32(acc + lane_base + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i;
+          if (c < a.Z) { if (gw) atomicAdd(gw + static_cast<size_t>(j) * ld + col_off + c, __uint_as_float(v[i]) * inv_gs); }
+          else if (c == a.Z) { if (gb) atomicAdd(gb + j, __uint_as_float(v[i]) * inv_gs); }
+        }
+      }
+    };
+    if (kindA) {
+      flush_h(tmem + 0, a.g_mod_w[1], H + a.Z, 0);
+      flush_z(tmem + 128, a.g_mod_w[1], H + a.Z, H, a.g_mod_b[1]);
+      flush_h(tmem + 128 + a.ZP, a.g_siren_w[1], H, 0);
+    } else {
+      flush_z(tmem + 0, a.g_mod_w[0], a.Z, 0, a.g_mod_b[0]);
+      flush_h(tmem + a.ZP, a.g_mod_w[2], H + a.Z, 0);
+      flush_z(tmem + a.ZP + 128, a.g_mod_w[2], H + a.Z, H, a.g_mod_b[2]);
+      flush_h(tmem + 2 * a.ZP + 128, a.g_siren_w[2], H, 0);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// Loss-scale plumbing
+// ------------------------------------------------------------------------------------------
+__global__ void set_gscale_kernel(float* g, float gs, float mult) { g[0] = gs; g[1] = 1.0f / gs; g[2] = mult; }
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* out) {
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+__global__ void gscale_from_absmax_kernel(const unsigned int* mx, float* g) {
+  const float m = __uint_as_float(*mx);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) frexpf(m, &e);   // m = f * 2^e, f in [0.5,1)
+  const float gs = ldexpf(1.0f, 1 - e);          // max|dout| * gs in [1, 2)
+  g[0] = gs; g[1] = 1.0f / gs; g[2] = 0.f;
+}
+
+// Backward weight stream per tile: [Ws2^T][W2h^T][W2z^T] [Ws1^T][W1h^T][W1z^T] [W0z^T], each as two 64-wide
+// K panels (K = output features) of a [N = input features, 128] matrix.
+int pack_backward_panels(const nvp_desc* d, const nvp_params* p, PackArgs& a, uint32_t base_off, BwdArgs* b) {
+  const Dims m = make_dims(d);
+  uint32_t off = base_off;
+  int k = 0;
+  auto add = [&](const float* src, int ld, int r0, int rvalid, int rows) {
+    for (int q = 0; q < 2; ++q) {
+      b->poff[k] = off - base_off; b->pbytes[k] = static_cast<uint32_t>(rows) * 128u; ++k;
+      add_panel(a, src, ld, 1, r0, 64 * q, rvalid, 64, rows, off);
+    }
+  };
+  for (int i = 2; i >= 1; --i) {
+    add(p->siren_w[i], H, 0, H, H);
+    add(p->mod_w[i], H + m.Z, 0, H, H);
+    add(p->mod_w[i], H + m.Z, H, m.Z, m.ZP);
+  }
+  add(p->mod_w[0], m.Z, 0, m.Z, m.ZP);
+  return 0;
+}
+
 struct TcWorkspace {
   uint8_t* wpk_fwd;
+  uint8_t* wpk_bwd;
   uint8_t* z16t;
   uint8_t* stash;
+  uint8_t* dpre;
+  float* dz;
   float* rgb;
+  float* gscale;
   size_t total;
 };
 TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
@@ -368,9 +917,15 @@ TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
   };
   TcWorkspace w{};
   w.wpk_fwd = take(m.fwd_bytes);
+  w.wpk_bwd = take(static_cast<size_t>(8) * kPanelBytes + static_cast<size_t>(6) * m.ZP * 128);
   w.z16t = take(static_cast<size_t>(tiles) * m.KZ * kPanelBytes);
   w.rgb = reinterpret_cast<float*>(take(static_cast<size_t>(tiles) * kTile * 3 * sizeof(float)));
-  if (what == 1) w.stash = take(static_cast<size_t>(tiles) * SL_COUNT * 2 * kPanelBytes);
+  if (what == 1) {
+    w.stash = take(static_cast<size_t>(tiles) * SL_COUNT * 2 * kPanelBytes);
+    w.dpre = take(static_cast<size_t>(tiles) * DP_COUNT * 2 * kPanelBytes);
+    w.dz = reinterpret_cast<float*>(take(static_cast<size_t>(tiles) * kTile * m.ZP * sizeof(float)));
+    w.gscale = reinterpret_cast<float*>(take(64));
+  }
   w.total = off + 1024;
   return w;
 }
@@ -385,6 +940,8 @@ int num_sms() {
   return sms;
 }
 
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+
 int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w, const float* tsteps, int64_t n,
                    float* rgb, bool train, cudaStream_t st) {
   const Dims m = make_dims(d);
@@ -395,13 +952,13 @@ int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w,
   a.w0 = d->w0_first; a.rgb = rgb; a.stash = w.stash; a.n = n;
   a.n_tiles = static_cast<int>((n + kTile - 1) / kTile);
   a.KZ = m.KZ; a.npf = m.npf;
-  const int budget = 227 * 1024 - 2048;
   a.nstage = 0;
   for (int ns = 12; ns >= 2; --ns)
-    if (static_cast<int>(fwd_smem_layout(m.KZ, ns).total) <= budget) { a.nstage = ns; break; }
+    if (static_cast<int>(fwd_smem_layout(m.KZ, ns).total) <= kSmemBudget) { a.nstage = ns; break; }
   NVP_CHECK(a.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core path");
   const size_t smem = fwd_smem_layout(m.KZ, a.nstage).total + 1024;
   const int grid = std::min(a.n_tiles, num_sms());
+  ScopedKernelTimer timer(K_MLP_FWD, st);
   if (train) {
     NVP_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     mlp_forward_kernel<true><<<grid, kThreads, smem, st>>>(a);
@@ -424,15 +981,86 @@ int tc_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   const TcWorkspace w = carve_tc(d, n, 0, base);
   const Dims m = make_dims(d);
   int rc;
-  if ((rc = pack_forward_weights(d, p, w.wpk_fwd, st))) return rc;
+  if ((rc = pack_forward_weights(d, p, w.wpk_fwd, nullptr, st))) return rc;
   if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st))) return rc;
   return launch_forward(d, p, w, tsteps, n, out_rgb, false, st);
 }
 
-int tc_fwd_bwd(const nvp_desc*, const LevelTab&, const nvp_params*, const float*, const float*, const uint8_t*,
-               const float*, int64_t, int64_t, const nvp_grads*, float*, float*, void*, size_t, cudaStream_t) {
-  set_error("NVP_MODE_TC_F16 backward not built yet");
-  return 9;
+int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, const float* tsteps,
+               const uint8_t* gt_u8, const float* dout, int64_t n, int64_t n_global, const nvp_grads* g, float* loss_sum,
+               float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st) {
+  NVP_CHECK(ws_bytes >= tc_workspace_bytes(d, n, 1), "workspace too small (see nvp_workspace_bytes)");
+  const Dims m = make_dims(d);
+  NVP_CHECK(2 * m.ZP + 256 <= 512, "tensor-core backward: latent wider than 127 columns (config L) is not built yet");
+  void* base = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  const TcWorkspace w = carve_tc(d, n, 1, base);
+  const int n_tiles = static_cast<int>((n + kTile - 1) / kTile);
+  int rc;
+
+  // 1. loss scale
+  if (dout == nullptr) {
+    const double target = 1.5 * static_cast<double>(n_global);
+    const float gs = ldexpf(1.0f, static_cast<int>(lrint(log2(target))));
+    set_gscale_kernel<<<1, 1, 0, st>>>(w.gscale, gs, gs * 2.0f / (3.0f * static_cast<float>(n_global)));
+    NVP_LAUNCH_CHECK();
+  } else {
+    unsigned int* mx = reinterpret_cast<unsigned int*>(w.gscale + 8);
+    NVP_CUDA(cudaMemsetAsync(mx, 0, sizeof(unsigned int), st));
+    absmax_kernel<<<std::min<int64_t>(1024, (3 * n + 255) / 256), 256, 0, st>>>(dout, 3 * n, mx);
+    NVP_LAUNCH_CHECK();
+    gscale_from_absmax_kernel<<<1, 1, 0, st>>>(mx, w.gscale);
+    NVP_LAUNCH_CHECK();
+  }
+
+  // 2. weights -> fp16 panels (forward and backward streams in one launch)
+  BwdArgs b{};
+  if ((rc = pack_forward_weights(d, p, w.wpk_fwd, &b, st, w.wpk_bwd))) return rc;
+
+  // 3. positional features, 4. fused forward (keeps the activation stash)
+  if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st))) return rc;
+  float* rgb = out_rgb ? out_rgb : w.rgb;
+  if ((rc = launch_forward(d, p, w, tsteps, n, rgb, true, st))) return rc;
+
+  // 5. fused backward
+  b.wpk = w.wpk_bwd; b.stash = w.stash; b.tau = tsteps; b.rgb = rgb; b.gt = gt_u8; b.dout = dout; b.gscale = w.gscale;
+  b.siren_w0 = p->siren_w[0]; b.siren_b0 = p->siren_b[0]; b.last_w = p->last_w; b.w0 = d->w0_first;
+  b.dpre = w.dpre; b.dz = w.dz; b.loss_sum = loss_sum;
+  b.g_last_w = g->last_w; b.g_last_b = g->last_b; b.g_siren_b1 = g->siren_b[1]; b.g_siren_b2 = g->siren_b[2];
+  b.g_siren_w0 = g->siren_w[0]; b.g_siren_b0 = g->siren_b[0];
+  b.n = n; b.n_tiles = n_tiles; b.ZP = m.ZP;
+  b.stage_bytes = static_cast<uint32_t>(m.ZP) * 128u;
+  b.nstage = 0;
+  for (int ns = 12; ns >= 2; --ns)
+    if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes).total) <= kSmemBudget) { b.nstage = ns; break; }
+  NVP_CHECK(b.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core backward");
+  {
+    const size_t smem = bwd_smem_layout(b.nstage, b.stage_bytes).total + 1024;
+    NVP_CUDA(cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ScopedKernelTimer timer(K_MLP_BWD, st);
+    mlp_backward_kernel<<<std::min(n_tiles, num_sms()), kThreads, smem, st>>>(b);
+    NVP_LAUNCH_CHECK();
+  }
+
+  // 6. weight gradients
+  {
+    WgArgs wa{};
+    wa.dpre = w.dpre; wa.stash = w.stash; wa.z16t = w.z16t; wa.gscale = w.gscale;
+    for (int i = 0; i < 3; ++i) { wa.g_mod_w[i] = g->mod_w[i]; wa.g_mod_b[i] = g->mod_b[i]; wa.g_siren_w[i] = g->siren_w[i]; }
+    wa.n_units = 2 * n_tiles; wa.KZ = m.KZ; wa.Z = m.Z; wa.ZP = m.ZP;
+    const int sms = num_sms();
+    int na = std::max(1, std::min(wa.n_units, (sms * 45) / 100));
+    int nb = std::max(1, std::min(wa.n_units, sms - na));
+    wa.n_a = na;
+    const size_t smem = 2 * static_cast<size_t>(10 + m.KZ) * kHalfPanelBytes + 1024;
+    NVP_CHECK(static_cast<int>(smem) <= kSmemBudget + 1024, "latent too wide for the wgrad shared-memory plan");
+    NVP_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ScopedKernelTimer timer(K_MLP_WGRAD, st);
+    mlp_wgrad_kernel<<<na + nb, kWgThreads, smem, st>>>(wa);
+    NVP_LAUNCH_CHECK();
+  }
+
+  // 7. scatter-add into the grids (dz is still multiplied by gs)
+  return launch_grid_scatter(d, tab, coords, n, w.dz, m.ZP, 1.0f, w.gscale + 1, g, st);
 }
 
 }  // namespace nvp

@@ -3,6 +3,8 @@
 // check the UMMA descriptors, the manual 128-byte swizzle and the TMEM read-back on real hardware.
 //   mode 0 (K-major operands) : D = A[128,K] * B[128,K]^T          K % 64 == 0, K <= 256
 //   mode 1 (MN-major operands): D = A[K,128]^T * B[K,128]          K % 16 == 0, K <= 128
+//   mode 2+x, x in 0..3 (skinny): D[:, 0:16] = A[K,128]^T * B[K, 16x : 16x+16]   (N = 16, B start offset
+//                               inside the 128-byte swizzle atom: the column-sum / small-gradient trick)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -62,11 +64,17 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __rest
         for (int kk = 0; kk < 4; ++kk)
           umma_f16_ss(tmem, umma_desc_kmajor(smem_u32(sA + p * kPanelBytes), kk),
                       umma_desc_kmajor(smem_u32(sB + p * kPanelBytes), kk), idesc, (p | kk) ? 1u : 0u);
-    } else {
+    } else if (mode == 1) {
       const uint32_t idesc = umma_idesc_f16(128, 128, true, true);
       for (int kk = 0; kk < K / 16; ++kk)
         umma_f16_ss(tmem, umma_desc_mnmajor(smem_u32(sA), kk, kPanelBytes), umma_desc_mnmajor(smem_u32(sB), kk, kPanelBytes),
                     idesc, kk ? 1u : 0u);
+    } else {
+      const uint32_t idesc = umma_idesc_f16(128, 16, true, true);
+      const uint32_t boff = static_cast<uint32_t>(mode - 2) * 32u;
+      for (int kk = 0; kk < K / 16; ++kk)
+        umma_f16_ss(tmem, umma_desc_mnmajor(smem_u32(sA), kk, kPanelBytes),
+                    umma_desc_mnmajor(smem_u32(sB) + boff, kk, kPanelBytes), idesc, kk ? 1u : 0u);
     }
     umma_commit(&bar);
   }
@@ -89,9 +97,9 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __rest
 
 extern "C" int nvp_selftest_umma(const void* A, const void* B, float* D, int K, int mode, void* stream) {
   using namespace nvp;
-  NVP_CHECK(mode == 0 || mode == 1, "mode must be 0 or 1");
+  NVP_CHECK(mode >= 0 && mode <= 5, "mode must be in [0,5]");
   if (mode == 0) NVP_CHECK(K % 64 == 0 && K >= 64 && K <= 256, "mode 0 needs K in {64,128,192,256}");
-  if (mode == 1) NVP_CHECK(K % 16 == 0 && K >= 16 && K <= 128, "mode 1 needs K % 16 == 0, K <= 128");
+  if (mode >= 1) NVP_CHECK(K % 16 == 0 && K >= 16 && K <= 128, "mode 1 needs K % 16 == 0, K <= 128");
   const int npan = mode == 0 ? K / 64 : 2;
   const size_t smem = static_cast<size_t>(2 * npan) * tc::kPanelBytes + 1024;
   NVP_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

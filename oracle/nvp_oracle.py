@@ -163,25 +163,40 @@ def sparse_grid_forward(emb: torch.Tensor, coords: torch.Tensor) -> torch.Tensor
 # --------------------------------------------------------------------------------------------
 # Modulated SIREN (modulation.py)
 # --------------------------------------------------------------------------------------------
-def modulator_forward(z: torch.Tensor, p: Dict[str, torch.Tensor], n_layers: int = 3):
+def _operand(x: torch.Tensor, mma_dtype) -> torch.Tensor:
+    """Round a GEMM operand to the tensor-core operand type (straight-through for autograd).
+
+    mma_dtype=None is the reference arithmetic.  mma_dtype=torch.float16 restates the product's
+    NVP_MODE_TC_F16 forward (fp16 operands, wide accumulation) so tests can separate arithmetic-mode
+    effects (LeakyReLU sign flips of near-zero pre-activations) from kernel bugs."""
+    if mma_dtype is None:
+        return x
+    return x + (x.to(mma_dtype).to(x.dtype) - x).detach()
+
+
+def modulator_forward(z: torch.Tensor, p: Dict[str, torch.Tensor], n_layers: int = 3, mma_dtype=None):
     hs = []
     x = z
     for i in range(n_layers):
         W = p[f"wrapper.modulator.layers.{i}.0.weight"]
         b = p[f"wrapper.modulator.layers.{i}.0.bias"]
-        h = torch.nn.functional.leaky_relu(x @ W.t() + b, 0.01)
+        h = torch.nn.functional.leaky_relu(_operand(x, mma_dtype) @ _operand(W, mma_dtype).t() + b, 0.01)
         hs.append(h)
         x = torch.cat((h, z), dim=1)
     return hs
 
 
-def siren_forward(tau: torch.Tensor, mods, p: Dict[str, torch.Tensor], n_layers: int = 3, w0_initial: float = 30.0):
+def siren_forward(tau: torch.Tensor, mods, p: Dict[str, torch.Tensor], n_layers: int = 3, w0_initial: float = 30.0,
+                  mma_dtype=None):
     x = tau
     for i in range(n_layers):
         W = p[f"net.layers.{i}.weight"]
         b = p[f"net.layers.{i}.bias"]
         w0 = w0_initial if i == 0 else 1.0
-        x = torch.sin(w0 * (x @ W.t() + b))
+        if i == 0:
+            x = torch.sin(w0 * (x @ W.t() + b))  # K = 1: CUDA cores in every mode
+        else:
+            x = torch.sin(w0 * (_operand(x, mma_dtype) @ _operand(W, mma_dtype).t() + b))
         x = x * mods[i]
     return x @ p["net.last_layer.weight"].t() + p["net.last_layer.bias"]
 
@@ -238,11 +253,12 @@ def latent_forward(p: Dict[str, torch.Tensor], coords: torch.Tensor, cfg: NVPCon
     return torch.cat((xy, yt, xt, sg), dim=1)
 
 
-def nvp_forward(p: Dict[str, torch.Tensor], coords: torch.Tensor, tsteps: torch.Tensor, cfg: NVPConfig) -> torch.Tensor:
+def nvp_forward(p: Dict[str, torch.Tensor], coords: torch.Tensor, tsteps: torch.Tensor, cfg: NVPConfig,
+                mma_dtype=None) -> torch.Tensor:
     """coords [N,3]=(t,x,y), tsteps [N] -> rgb [N,3]."""
     z = latent_forward(p, coords, cfg)
-    mods = modulator_forward(z, p, cfg.n_hidden_layers)
-    return siren_forward(tsteps.reshape(-1, 1).to(z.dtype), mods, p, cfg.n_hidden_layers)
+    mods = modulator_forward(z, p, cfg.n_hidden_layers, mma_dtype)
+    return siren_forward(tsteps.reshape(-1, 1).to(z.dtype), mods, p, cfg.n_hidden_layers, mma_dtype=mma_dtype)
 
 
 def normalise_gt(img_u8: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
@@ -308,14 +324,15 @@ def init_params(cfg: NVPConfig, seed: int = 0, grid_std: float = 1e-4, dtype=tor
 
 def nvp_loss_and_grads(p: Dict[str, torch.Tensor], coords: torch.Tensor, tsteps: torch.Tensor,
                        gt_u8: torch.Tensor, cfg: NVPConfig, n_global: Optional[int] = None,
-                       dtype=torch.float32) -> Tuple[torch.Tensor, float, Dict[str, torch.Tensor]]:
+                       dtype=torch.float32, mma_dtype=None) -> Tuple[torch.Tensor, float, Dict[str, torch.Tensor]]:
     """Forward + MSE + backward of the restated path.  Returns (rgb, loss, grads).
 
     n_global: denominator of the mean is 3*n_global (for a shard of a larger batch); default N.
-    dtype=float64 gives a high-precision reference for tolerance budgeting.
+    dtype=float64 gives a high-precision reference for tolerance budgeting; mma_dtype=torch.float16
+    restates the tensor-core mode's forward operand rounding (see _operand).
     """
     q = {k: v.detach().to(dtype).requires_grad_(True) for k, v in p.items()}
-    rgb = nvp_forward(q, coords.to(dtype), tsteps.to(dtype), cfg)
+    rgb = nvp_forward(q, coords.to(dtype), tsteps.to(dtype), cfg, mma_dtype)
     gt = normalise_gt(gt_u8.reshape(-1, 3), dtype)
     n = rgb.shape[0] if n_global is None else n_global
     loss = ((rgb - gt) ** 2).sum() / (3.0 * n)

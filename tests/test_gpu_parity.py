@@ -16,7 +16,48 @@ pytestmark = pytest.mark.gpu
 
 MODES = ["fp32", "tc"]
 FWD_TOL = {"fp32": 2e-5, "tc": 1e-3}
-GRAD_TOL = {"fp32": 2e-4, "tc": 2e-2}
+# Gradient tolerances, relative to the largest reference entry of each tensor.
+#   fp32 mode: fp32 round-off against the fp64 oracle.
+#   tc mode:   (a) against the oracle restated with the mode's own forward arithmetic (fp16 GEMM operands,
+#              oracle mma_dtype=float16): max error 1e-2 (fp16 rounding of the backward operands);
+#              (b) against the exact fp64 oracle: L2-relative 3e-2.  A max-norm bound is not meaningful there:
+#              fp16 forward rounding flips the sign of near-zero LeakyReLU pre-activations, which changes that
+#              unit's derivative by 100x (1 vs 0.01) for a handful of (sample, unit) pairs.
+GRAD_TOL = {"fp32": 2e-4, "tc": 1e-2}
+GRAD_L2_TOL_EXACT = 3e-2
+
+
+def l2_rel(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def assert_grads(got, ref_exact, mode, ref_mode=None, tag=""):
+    """got/ref: dict name -> tensor.  ref_mode = oracle grads with the mode's forward arithmetic (tc only)."""
+    for k, ref in ref_exact.items():
+        if mode == "fp32":
+            assert rel_err(got[k], ref) <= GRAD_TOL[mode], (k, tag, rel_err(got[k], ref))
+        else:
+            assert l2_rel(got[k], ref) <= GRAD_L2_TOL_EXACT, (k, tag, "l2 vs exact", l2_rel(got[k], ref))
+            if ref_mode is not None:
+                assert rel_err(got[k], ref_mode[k]) <= GRAD_TOL[mode], (k, tag, "vs fp16-operand oracle", rel_err(got[k], ref_mode[k]))
+
+
+def golden_grad_refs(g, cfg, p, mode):
+    """exact grads from the fixture (+ the fp16-operand oracle recomputed on CPU for the tc mode)."""
+    exact = {}
+    for k, v in p.items():
+        if k in O.PARAM_KEYS_GRID:
+            ref = torch.zeros(v.numel(), dtype=torch.float64)
+            ref[torch.from_numpy(g["gidx:" + k])] = torch.from_numpy(g["gval:" + k]).double()
+        else:
+            ref = torch.from_numpy(g["grad:" + k]).double()
+        exact[k] = ref
+    ref_mode = None
+    if mode == "tc":
+        _, _, ref_mode = O.nvp_loss_and_grads(p, torch.from_numpy(g["coords"]), torch.from_numpy(g["tsteps"]),
+                                              torch.from_numpy(g["gt"]), cfg, dtype=torch.float64, mma_dtype=torch.float16)
+    return exact, ref_mode
 
 
 def dev(t):
@@ -54,40 +95,29 @@ def test_forward_matches_golden(name, mode):
     assert err <= FWD_TOL[mode], err
 
 
-def check_grads(got, g, cfg, tol):
-    for k, v in got.items():
-        if k.startswith("wrapper.net."):
-            continue
-        v = v.reshape(-1).double()
-        if k in O.PARAM_KEYS_GRID:
-            ref = torch.zeros_like(v)
-            ref[torch.from_numpy(g["gidx:" + k])] = torch.from_numpy(g["gval:" + k]).double()
-        else:
-            ref = torch.from_numpy(g["grad:" + k]).double()
-        e = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-30)
-        assert e <= tol, (k, e)
-
-
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_autograd_backward_matches_golden(name, mode):
     """model(x) -> image_mse -> backward, exactly as training.py:50-52,74 drives it."""
     g, cfg = load_golden(name)
-    m = make_model(cfg, golden_params(g, cfg), mode=mode)
+    p = golden_params(g, cfg)
+    m = make_model(cfg, p, mode=mode)
     x = {"all_coords": dev(torch.from_numpy(g["coords"]))[None], "temporal_steps": dev(torch.from_numpy(g["tsteps"]))[None]}
     gt = (dev(torch.from_numpy(g["gt"])).float() - 127.5) / 127.5
     out = m(x)["model_out"]
     loss = ((out - gt[None]) ** 2).mean()
     loss.backward()
-    assert abs(float(loss) - float(g["loss64"])) <= (1e-5 if mode == "fp32" else 2e-3)
-    check_grads(model_grads(m), g, cfg, GRAD_TOL[mode])
+    assert abs(float(loss.detach()) - float(g["loss64"])) <= (1e-5 if mode == "fp32" else 2e-3)
+    exact, ref_mode = golden_grad_refs(g, cfg, p, mode)
+    assert_grads(model_grads(m), exact, mode, ref_mode, name)
 
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_fused_step_matches_golden(name, mode):
     g, cfg = load_golden(name)
-    m = make_model(cfg, golden_params(g, cfg), mode=mode)
+    p = golden_params(g, cfg)
+    m = make_model(cfg, p, mode=mode)
     x = {"all_coords": dev(torch.from_numpy(g["coords"]))[None], "temporal_steps": dev(torch.from_numpy(g["tsteps"]))[None]}
     n = g["coords"].shape[0]
     rgb = torch.empty(n, 3, device="cuda")
@@ -95,7 +125,8 @@ def test_fused_step_matches_golden(name, mode):
     loss = float(ls) / (3 * n)
     assert abs(loss - float(g["loss64"])) <= (1e-5 if mode == "fp32" else 2e-3)
     assert np.abs(rgb.cpu().numpy() - g["rgb64"]).max() <= FWD_TOL[mode]
-    check_grads(model_grads(m), g, cfg, GRAD_TOL[mode])
+    exact, ref_mode = golden_grad_refs(g, cfg, p, mode)
+    assert_grads(model_grads(m), exact, mode, ref_mode, name)
     # gradients accumulate (caller zeroes): a second identical call doubles them
     before = {k: v.clone() for k, v in model_grads(m).items()}
     m.fwd_loss_bwd(x, dev(torch.from_numpy(g["gt"])))
@@ -111,15 +142,16 @@ def test_ragged_batch_sizes_against_oracle(n, mode):
     p = O.init_params(cfg, seed=n, grid_std=0.3)
     coords, tsteps, gt = sampler_like_inputs(cfg, n, seed=n + 1)
     rgb_ref, loss_ref, grads_ref = O.nvp_loss_and_grads(p, coords, tsteps, gt, cfg, dtype=torch.float64)
+    ref_mode = None
+    if mode == "tc":
+        ref_mode = O.nvp_loss_and_grads(p, coords, tsteps, gt, cfg, dtype=torch.float64, mma_dtype=torch.float16)[2]
     m = make_model(cfg, p, mode=mode)
     x = {"all_coords": dev(coords)[None], "temporal_steps": dev(tsteps)[None]}
     rgb = torch.empty(n, 3, device="cuda")
     ls = m.fwd_loss_bwd(x, dev(gt), out_rgb=rgb)
     assert float((rgb.cpu().double() - rgb_ref).abs().max()) <= FWD_TOL[mode]
     assert abs(float(ls) / (3 * n) - loss_ref) <= (1e-5 if mode == "fp32" else 2e-3)
-    got = model_grads(m)
-    for k, ref in grads_ref.items():
-        assert rel_err(got[k], ref) <= GRAD_TOL[mode], (k, n)
+    assert_grads(model_grads(m), grads_ref, mode, ref_mode, f"n={n}")
 
 
 def test_empty_batch_is_a_noop():
