@@ -10,6 +10,8 @@
 // loads are warp-broadcasts.  Threads with level index < 9 also fetch one voxel of the 3x3
 // neighbourhood.  All table reads go through the read-only path as F-wide vectors; the backward
 // uses F-wide vector reductions (red.global.add.v2/v4.f32, sm_90+).
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -90,6 +92,10 @@ struct GridArgs {
   int tres, xres, yres;
   float scale;
   const float* scale_ptr;  // optional device scalar multiplied into scale
+  int lvl_begin;           // scatter: keyframe levels [lvl_begin, L) go straight to global memory
+  int n_coarse;            // coarse kernel: levels [0, n_coarse) are privatised in shared memory
+  int coarse_cells;        // offset[n_coarse]
+  int64_t chunk;           // coarse kernel: samples per CTA
 };
 
 struct SampleGeom {
@@ -279,17 +285,18 @@ __global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridAr
   const float* dzr = a.z + s * a.ldz;
   const float scale = a.scale_ptr ? a.scale * __ldg(a.scale_ptr) : a.scale;
   float d[F2];
-  if (a.gkf[0] != nullptr) {
+  const bool fine = l >= a.lvl_begin;  // coarser levels are handled by grid_scatter_coarse_kernel
+  if (a.gkf[0] != nullptr && fine) {
 #pragma unroll
     for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + l * F2 + f) * scale;
     plane_scatter<F2>(a.gkf[0], off, res, ix, wx, iy, wy, d);
   }
-  if (a.gkf[1] != nullptr) {
+  if (a.gkf[1] != nullptr && fine) {
 #pragma unroll
     for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + l * F2 + f) * scale;
     plane_scatter<F2>(a.gkf[1], off, res, it, wt, iy, wy, d);
   }
-  if (a.gkf[2] != nullptr) {
+  if (a.gkf[2] != nullptr && fine) {
 #pragma unroll
     for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + l * F2 + f) * scale;
     plane_scatter<F2>(a.gkf[2], off, res, it, wt, ix, wx, d);
@@ -306,6 +313,101 @@ __global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridAr
       red_feat<F3>(a.gsparse + vox * F3, dv);
     }
   }
+}
+
+// Coarse keyframe levels receive millions of reductions into a few hundred cells each (level 0: 256 cells,
+// 4 corners x 1.2 M samples x 3 planes); as global reductions they serialise in L2 (measured: level 0 alone
+// 1.0 ms of a 2.8 ms scatter).  This kernel keeps a private copy of levels [0, n_coarse) of all three planes
+// in shared memory per persistent CTA, accumulates with shared-memory atomics and flushes each CTA's
+// non-zero partial sums once.
+constexpr int kCoarseThreads = 512;
+
+template <int F2>
+__device__ __forceinline__ void plane_scatter_smem(float* __restrict__ tab, int off, int res, int i0, float w0, int i1,
+                                                   float w1, const float (&d)[F2]) {
+  const int cells = res * res;
+  float* base = tab + static_cast<size_t>(off) * F2;
+  const int b00 = i0 + i1 * res;
+  const int c00 = wrap_cell(b00, cells), c10 = wrap_cell(b00 + 1, cells);
+  const int c01 = wrap_cell(b00 + res, cells), c11 = wrap_cell(b00 + res + 1, cells);
+  const float a0 = 1.0f - w0, a1 = 1.0f - w1;
+  const float k00 = a0 * a1, k10 = w0 * a1, k01 = a0 * w1, k11 = w0 * w1;
+#pragma unroll
+  for (int f = 0; f < F2; ++f) {
+    atomicAdd(base + c00 * F2 + f, k00 * d[f]);
+    atomicAdd(base + c10 * F2 + f, k10 * d[f]);
+    atomicAdd(base + c01 * F2 + f, k01 * d[f]);
+    atomicAdd(base + c11 * F2 + f, k11 * d[f]);
+  }
+}
+
+template <int F2>
+__global__ void __launch_bounds__(kCoarseThreads) grid_scatter_coarse_kernel(const GridArgs a) {
+  extern __shared__ float s_tab[];  // [3 planes][coarse_cells][F2]
+  __shared__ float s_scale[NVP_MAX_LEVELS];
+  __shared__ int s_res[NVP_MAX_LEVELS];
+  __shared__ int s_off[NVP_MAX_LEVELS];
+  const int LC = a.n_coarse;
+  if (threadIdx.x < LC) {
+    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
+    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
+    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
+  }
+  const int plane_floats = a.coarse_cells * F2;
+  for (int i = threadIdx.x; i < 3 * plane_floats; i += kCoarseThreads) s_tab[i] = 0.0f;
+  __syncthreads();
+
+  const int pw = a.tab.n_levels * F2;
+  const float scale = a.scale_ptr ? a.scale * __ldg(a.scale_ptr) : a.scale;
+  const int spp = kCoarseThreads / LC;  // samples per pass
+  const int ls = threadIdx.x / LC, l = threadIdx.x - ls * LC;
+  const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * a.chunk;
+  const int64_t s_end = min(a.n, s_begin + a.chunk);
+  if (ls < spp) {
+    const float sc = s_scale[l];
+    const int res = s_res[l], off = s_off[l];
+    for (int64_t s = s_begin + ls; s < s_end; s += spp) {
+      const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
+      int it, ix, iy;
+      float wt, wx, wy;
+      pos_fract(sc, t, it, wt);
+      pos_fract(sc, x, ix, wx);
+      pos_fract(sc, y, iy, wy);
+      const float* dzr = a.z + s * a.ldz + l * F2;
+      float d[F2];
+      if (a.gkf[0] != nullptr) {
+#pragma unroll
+        for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + f) * scale;
+        plane_scatter_smem<F2>(s_tab, off, res, ix, wx, iy, wy, d);
+      }
+      if (a.gkf[1] != nullptr) {
+#pragma unroll
+        for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + f) * scale;
+        plane_scatter_smem<F2>(s_tab + plane_floats, off, res, it, wt, iy, wy, d);
+      }
+      if (a.gkf[2] != nullptr) {
+#pragma unroll
+        for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + f) * scale;
+        plane_scatter_smem<F2>(s_tab + 2 * plane_floats, off, res, it, wt, ix, wx, d);
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < 3; ++p) {
+    if (a.gkf[p] == nullptr) continue;
+    for (int i = threadIdx.x; i < plane_floats; i += kCoarseThreads) {
+      const float v = s_tab[p * plane_floats + i];
+      if (v != 0.0f) atomicAdd(a.gkf[p] + i, v);
+    }
+  }
+}
+
+template <int F2>
+int launch_coarse(const GridArgs& a, int blocks, size_t smem, cudaStream_t st) {
+  NVP_CUDA(cudaFuncSetAttribute(grid_scatter_coarse_kernel<F2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  grid_scatter_coarse_kernel<F2><<<blocks, kCoarseThreads, smem, st>>>(a);
+  return 0;
 }
 
 template <int F2, int F3>
@@ -374,6 +476,34 @@ int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coo
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
   a.scale = scale;
   a.scale_ptr = scale_ptr;
+  // Coarse levels -> shared-memory privatised kernel (as many levels as fit ~150 KB for three planes).
+  a.lvl_begin = 0;
+  const bool any_kf = g->kf_xy || g->kf_yt || g->kf_xt;
+  if (any_kf && n >= 4096) {
+    int lc = 0;
+    while (lc < tab.n_levels && static_cast<size_t>(tab.offset[lc + 1]) * d->n_features * 3 * sizeof(float) <= 150 * 1024) ++lc;
+    if (lc > 0) {
+      a.n_coarse = lc;
+      a.coarse_cells = tab.offset[lc];
+      a.lvl_begin = lc;
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int blocks = static_cast<int>(std::min<int64_t>(sms, (n + 1023) / 1024));
+      a.chunk = (n + blocks - 1) / blocks;
+      const size_t smem = static_cast<size_t>(a.coarse_cells) * d->n_features * 3 * sizeof(float);
+      ScopedKernelTimer timer(K_SCATTER, st);
+      int rc = 1;
+      switch (d->n_features) {
+        case 1: rc = launch_coarse<1>(a, blocks, smem, st); break;
+        case 2: rc = launch_coarse<2>(a, blocks, smem, st); break;
+        case 4: rc = launch_coarse<4>(a, blocks, smem, st); break;
+        case 8: rc = launch_coarse<8>(a, blocks, smem, st); break;
+      }
+      if (rc) return rc;
+      NVP_LAUNCH_CHECK();
+    }
+  }
   return dispatch(true, d->n_features, d->sparse_features, a, st);
 }
 

@@ -87,7 +87,8 @@ void add_panel(PackArgs& a, const float* src, int ld, int transpose, int r0, int
 struct BwdArgs;
 int pack_backward_panels(const nvp_desc* d, const nvp_params* p, PackArgs& a, uint32_t base_off, BwdArgs* b);
 
-// Forward stream: [W0z] | [W1h][W1z][Ws1] | [W2h][W2z][Ws2], each as 64-wide K panels of a [128 out x K] matrix.
+// Forward stream: [W0z] | [W1z][W1h p0][Ws1 p0][W1h p1][Ws1 p1] | [W2z][W2h p0][Ws2 p0][W2h p1][Ws2 p1], each a
+// 64-wide K panel of a [128 out x K] matrix, in the order the MMA warp consumes them.
 // When `b` is given the backward stream is packed by the same launch into `bwd_dst`.
 int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, BwdArgs* b, cudaStream_t st,
                          uint8_t* bwd_dst = nullptr) {
@@ -97,9 +98,11 @@ int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, B
   uint32_t off = 0;
   for (int q = 0; q < m.KZ; ++q) add_panel(a, p->mod_w[0], m.Z, 0, 0, 64 * q, H, m.Z - 64 * q, H, off);
   for (int i = 1; i < 3; ++i) {
-    for (int q = 0; q < 2; ++q) add_panel(a, p->mod_w[i], H + m.Z, 0, 0, 64 * q, H, 64, H, off);
     for (int q = 0; q < m.KZ; ++q) add_panel(a, p->mod_w[i], H + m.Z, 0, 0, H + 64 * q, H, m.Z - 64 * q, H, off);
-    for (int q = 0; q < 2; ++q) add_panel(a, p->siren_w[i], H, 0, 0, 64 * q, H, 64, H, off);
+    for (int q = 0; q < 2; ++q) {
+      add_panel(a, p->mod_w[i], H + m.Z, 0, 0, 64 * q, H, 64, H, off);
+      add_panel(a, p->siren_w[i], H, 0, 0, 64 * q, H, 64, H, off);
+    }
   }
   if (b != nullptr) pack_backward_panels(d, p, a, static_cast<uint32_t>(bwd_dst - dst), b);
   ScopedKernelTimer timer(K_PACK, st);
@@ -155,35 +158,46 @@ struct FwdArgs {
 };
 
 struct FwdSmem {  // offsets into dynamic smem (1024-B aligned base)
-  uint32_t z, h, a, ring, consts, rgbx, bars, total;
+  uint32_t z, h, a, s, c, ring, consts, rgbx, bars, total;
 };
-__host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage) {
+__host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage, bool train) {
   FwdSmem s;
   uint32_t o = 0;
   s.z = o; o += KZ * kPanelBytes;
   s.h = o; o += 2 * kPanelBytes;
   s.a = o; o += 2 * kPanelBytes;
+  s.s = o; if (train) o += 2 * kPanelBytes;   // staging of sin / cos tiles for the TMA bulk store
+  s.c = o; if (train) o += 2 * kPanelBytes;
   s.ring = o; o += nstage * kPanelBytes;
   s.consts = o; o += (10 * H + 4) * 4;      // bm[3][H] bs[3][H] ws0[H] wl[3][H] bl[3]
-  s.rgbx = o; o += H * 3 * 4;               // partial rgb of the upper column half
+  s.rgbx = o; o += H * 3 * 4;               // partial rgb of the upper column sub-chunk
   s.bars = o; o += 64 * 8;
   s.total = o;
   return s;
 }
 
+// Forward kernel, v2 pipeline.
+//   * TMEM holds two accumulator sets (modulator / SIREN pre-activations, 4 x 128 columns): the GEMMs of
+//     step i+1 that do not depend on step i's epilogue (latent x W_z) run while that epilogue executes.
+//   * The epilogue works panel by panel (64 columns): as soon as panel p of h_i / a_i sits in shared
+//     memory the MMA warp issues the K-panel-p GEMMs of step i+1.
+//   * Train mode: every stashed activation tile is staged in shared memory in the MMA tile format and
+//     leaves through cp.async.bulk (TMA) stores, one 16 KiB panel at a time.
 template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const FwdSmem L = fwd_smem_layout(a.KZ, a.nstage);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const FwdSmem L = fwd_smem_layout(a.KZ, a.nstage, TRAIN);
   uint8_t* zbuf = smem + L.z;
   uint8_t* hbuf = smem + L.h;
   uint8_t* abuf = smem + L.a;
+  uint8_t* sbuf = smem + L.s;
+  uint8_t* cbuf = smem + L.c;
   uint8_t* ring = smem + L.ring;
   float* cst = reinterpret_cast<float*>(smem + L.consts);
   float* s_bm = cst;            // [3][H]
-  float* s_bs = cst + 3 * H;    // [3][H]
-  float* s_ws0 = cst + 6 * H;   // [H]
+  float* s_bs = cst + 3 * H;    // [3][H]   (layer 0 pre-multiplied by w0)
+  float* s_ws0 = cst + 6 * H;   // [H]      (pre-multiplied by w0)
   float* s_wl = cst + 7 * H;    // [3][H]
   float* s_bl = cst + 10 * H;   // [3]
   float* s_rgbx = reinterpret_cast<float*>(smem + L.rgbx);
@@ -193,29 +207,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
   uint64_t* zfull = bars + 32;
   uint64_t* zempty = bars + 33;
   uint64_t* acc_full = bars + 34;
-  uint64_t* epi_done = bars + 35;
+  uint64_t* panel_done = bars + 36;       // [3 steps][2 panels], one completion per tile each
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < 3 * H; i += kThreads) {
     s_bm[i] = __ldg(a.mod_b[i / H] + (i % H));
-    s_bs[i] = __ldg(a.siren_b[i / H] + (i % H));
+    s_bs[i] = __ldg(a.siren_b[i / H] + (i % H)) * (i < H ? a.w0 : 1.0f);
     s_wl[i] = __ldg(a.last_w + i);
   }
-  for (int i = tid; i < H; i += kThreads) s_ws0[i] = __ldg(a.siren_w0 + i);
+  for (int i = tid; i < H; i += kThreads) s_ws0[i] = __ldg(a.siren_w0 + i) * a.w0;
   if (tid < 3) s_bl[tid] = __ldg(a.last_b + tid);
   if (tid == 0) {
     for (int i = 0; i < a.nstage; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    mbar_init(zfull, 1); mbar_init(zempty, 1); mbar_init(acc_full, 1); mbar_init(epi_done, kEpiWarps);
+    mbar_init(zfull, 1); mbar_init(zempty, 1); mbar_init(acc_full, 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&panel_done[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&s_tmem, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t acc_m = tmem, acc_s = tmem + 128;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTile, H, false, false);
-      uint32_t g = 0, it = 0, n_epi = 0;
+      uint32_t g = 0, it = 0;
       auto gemm_panel = [&](uint32_t a_panel_addr, uint32_t acc, bool& first) {
         const uint32_t st = g % a.nstage, ph = (g / a.nstage) & 1;
         mbar_wait(&wfull[st], ph);
@@ -252,18 +266,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
         ++g;
       };
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(zfull, it & 1);
+        const uint32_t par = it & 1;
+        mbar_wait(zfull, par);
         for (int step = 0; step < 3; ++step) {
-          if (!(it == 0 && step == 0)) { mbar_wait(epi_done, n_epi & 1); ++n_epi; }
+          const uint32_t b = (3 * it + step) & 1;
+          const uint32_t acc_m = tmem + 128 * b, acc_s = tmem + 256 + 128 * b;
+          // accumulator set b was last read by the epilogue two steps ago; for step 1 that is the previous
+          // tile's last step, whose completion has not been observed yet.
+          if (step == 1 && it > 0) { mbar_wait(&panel_done[4], par ^ 1); mbar_wait(&panel_done[5], par ^ 1); }
           tcgen05_fence_after();
-          bool first = true;
-          if (step > 0)
-            for (int q = 0; q < 2; ++q) gemm_panel(smem_u32(hbuf + q * kPanelBytes), acc_m, first);
-          for (int q = 0; q < a.KZ; ++q) gemm_panel(smem_u32(zbuf + q * kPanelBytes), acc_m, first);
+          bool first_m = true, first_s = true;
+          for (int q = 0; q < a.KZ; ++q) gemm_panel(smem_u32(zbuf + q * kPanelBytes), acc_m, first_m);
           if (step == 2) umma_commit(zempty);
           if (step > 0) {
-            first = true;
-            for (int q = 0; q < 2; ++q) gemm_panel(smem_u32(abuf + q * kPanelBytes), acc_s, first);
+            for (int q = 0; q < 2; ++q) {
+              mbar_wait(&panel_done[(step - 1) * 2 + q], par);
+              tcgen05_fence_after();
+              gemm_panel(smem_u32(hbuf + q * kPanelBytes), acc_m, first_m);
+              gemm_panel(smem_u32(abuf + q * kPanelBytes), acc_s, first_s);
+            }
           }
           umma_commit(acc_full);
         }
@@ -272,24 +293,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
   } else {
     // ================= epilogue warps =================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;          // which 64-column half / output panel
+    const int sub = (warp - 2) >> 2;           // which 32-column half of the current 64-column panel
     const int r = quarter * 32 + lane;         // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t n_acc = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const bool issuer = (tid == 64);
+    uint32_t n_acc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int64_t s = static_cast<int64_t>(tile) * kTile + r;
       const bool valid = s < a.n;
       const float tau = valid ? __ldg(a.tau + s) : 0.0f;
       uint8_t* st_base = TRAIN ? a.stash + (static_cast<size_t>(tile) * SL_COUNT) * 2 * kPanelBytes : nullptr;
-      auto stash_ptr = [&](int slot) { return st_base + (static_cast<size_t>(slot) * 2 + half) * kPanelBytes; };
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       for (int step = 0; step < 3; ++step) {
+        const uint32_t b = (3 * it + step) & 1;
+        const uint32_t acc_m = tmem + 128 * b, acc_s = tmem + 256 + 128 * b;
         mbar_wait(acc_full, n_acc & 1); ++n_acc;
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int pc = cc * 32;            // column inside my panel
-          const int col = half * 64 + pc;    // column inside the layer
+        for (int p = 0; p < 2; ++p) {
+          const int pc = sub * 32;           // column inside panel p
+          const int col = p * 64 + pc;       // column inside the layer
+          if (TRAIN) {
+            // staging buffers of this panel were handed to the TMA two phases ago; at most the newest group may be pending
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          }
           uint32_t vm[32];
           tmem_ld32(acc_m + lane_base + col, vm);
           float hv[32], av[32];
@@ -298,8 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[col + i]);
-              const float sp = a.w0 * fmaf(tau, s_ws0[col + i], s_bs[col + i]);
-              av[i] = fast_sin(sp) * hv[i];
+              av[i] = fast_sin(fmaf(tau, s_ws0[col + i], s_bs[col + i])) * hv[i];
             }
           } else {
             uint32_t vs[32];
@@ -314,47 +341,50 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
               av[i] = sv[i] * hv[i];
             }
             if (TRAIN) {
-              store_row32(stash_ptr(step == 1 ? SL_S1 : SL_S2), r, pc, sv);
-              store_row32(stash_ptr(step == 1 ? SL_C1 : SL_C2), r, pc, cv);
+              store_row32(sbuf + p * kPanelBytes, r, pc, sv);
+              store_row32(cbuf + p * kPanelBytes, r, pc, cv);
             }
           }
+          if (step < 2 || TRAIN) store_row32(hbuf + p * kPanelBytes, r, pc, hv);
           if (step < 2) {
-            store_row32(hbuf + half * kPanelBytes, r, pc, hv);
-            store_row32(abuf + half * kPanelBytes, r, pc, av);
-            if (TRAIN) {
-              store_row32(stash_ptr(step == 0 ? SL_H0 : SL_H1), r, pc, hv);
-              store_row32(stash_ptr(step == 0 ? SL_A0 : SL_A1), r, pc, av);
-            }
+            store_row32(abuf + p * kPanelBytes, r, pc, av);
           } else {
-            if (TRAIN) store_row32(stash_ptr(SL_H2), r, pc, hv);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               rgb0 = fmaf(av[i], s_wl[col + i], rgb0);
               rgb1 = fmaf(av[i], s_wl[H + col + i], rgb1);
               rgb2 = fmaf(av[i], s_wl[2 * H + col + i], rgb2);
             }
+            if (p == 1 && sub == 1) { s_rgbx[r * 3] = rgb0; s_rgbx[r * 3 + 1] = rgb1; s_rgbx[r * 3 + 2] = rgb2; }
+          }
+          fence_proxy_async_smem();   // st.shared operand / staging tiles -> visible to UMMA and TMA (async proxy)
+          tcgen05_fence_before();
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (issuer) {
+            if (TRAIN) {
+              auto put = [&](int slot, const uint8_t* src) {
+                bulk_s2g(st_base + (static_cast<size_t>(slot) * 2 + p) * kPanelBytes, src + p * kPanelBytes, kPanelBytes);
+              };
+              if (step == 0) { put(SL_H0, hbuf); put(SL_A0, abuf); }
+              else if (step == 1) { put(SL_H1, hbuf); put(SL_A1, abuf); put(SL_S1, sbuf); put(SL_C1, cbuf); }
+              else { put(SL_H2, hbuf); put(SL_S2, sbuf); put(SL_C2, cbuf); }
+              bulk_commit();
+            }
+            mbar_arrive(&panel_done[step * 2 + p]);
           }
         }
-        if (step == 2) {
-          // combine the two column halves of each row: upper half hands its partial sums over
-          if (half == 1) { s_rgbx[r * 3] = rgb0; s_rgbx[r * 3 + 1] = rgb1; s_rgbx[r * 3 + 2] = rgb2; }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-          if (half == 0 && valid) {
-            a.rgb[s * 3] = rgb0 + s_rgbx[r * 3] + s_bl[0];
-            a.rgb[s * 3 + 1] = rgb1 + s_rgbx[r * 3 + 1] + s_bl[1];
-            a.rgb[s * 3 + 2] = rgb2 + s_rgbx[r * 3 + 2] + s_bl[2];
-          }
+        if (step == 2 && sub == 0 && valid) {
+          a.rgb[s * 3] = rgb0 + s_rgbx[r * 3] + s_bl[0];
+          a.rgb[s * 3 + 1] = rgb1 + s_rgbx[r * 3 + 1] + s_bl[1];
+          a.rgb[s * 3 + 2] = rgb2 + s_rgbx[r * 3 + 2] + s_bl[2];
         }
-        fence_proxy_async_smem();   // operand tiles written with st.shared -> visible to the UMMA (async proxy)
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done);
       }
     }
+    if (TRAIN && issuer) bulk_wait_all0();
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // ==========================================================================================
@@ -954,9 +984,9 @@ int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w,
   a.KZ = m.KZ; a.npf = m.npf;
   a.nstage = 0;
   for (int ns = 12; ns >= 2; --ns)
-    if (static_cast<int>(fwd_smem_layout(m.KZ, ns).total) <= kSmemBudget) { a.nstage = ns; break; }
+    if (static_cast<int>(fwd_smem_layout(m.KZ, ns, train).total) <= kSmemBudget) { a.nstage = ns; break; }
   NVP_CHECK(a.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core path");
-  const size_t smem = fwd_smem_layout(m.KZ, a.nstage).total + 1024;
+  const size_t smem = fwd_smem_layout(m.KZ, a.nstage, train).total + 1024;
   const int grid = std::min(a.n_tiles, num_sms());
   ScopedKernelTimer timer(K_MLP_FWD, st);
   if (train) {
