@@ -73,10 +73,11 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // 128-sample tile; see tc_common.cuh).
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
                        int64_t n, float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st);
-// grads += scatter of dz (fp32, pitch lddz) scaled by `scale` (times *scale_ptr when given).
+// grads += scatter of dz scaled by `scale` (times *scale_ptr when given).  dz is either fp32 row-major
+// (pitch lddz) or, when dz16t != NULL, fp16 in the MMA tile format with kz panels per 128-sample tile.
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
-                        const float* dz, int lddz, float scale, const float* scale_ptr, const nvp_grads* g,
-                        cudaStream_t st);
+                        const float* dz, int lddz, const uint8_t* dz16t, int kz, float scale, const float* scale_ptr,
+                        const nvp_grads* g, cudaStream_t st);
 
 // ---- mlp_simt.cu --------------------------------------------------------------------------
 size_t simt_workspace_bytes(const nvp_desc* d, int64_t n, int what);

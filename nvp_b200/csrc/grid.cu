@@ -92,6 +92,7 @@ struct GridArgs {
   int tres, xres, yres;
   float scale;
   const float* scale_ptr;  // optional device scalar multiplied into scale
+  const uint8_t* dz16t;    // scatter input in fp16 MMA tile format (kz panels per 128-sample tile) when non-null
   int lvl_begin;           // scatter: keyframe levels [lvl_begin, L) go straight to global memory
   int n_coarse;            // coarse kernel: levels [0, n_coarse) are privatised in shared memory
   int coarse_cells;        // offset[n_coarse]
@@ -151,6 +152,25 @@ __device__ __forceinline__ void plane_scatter(float* __restrict__ gtab, int off,
 #pragma unroll
   for (int f = 0; f < F2; ++f) v[f] = k11 * d[f];
   red_feat<F2>(base + static_cast<size_t>(c11) * F2, v);
+}
+
+// F consecutive columns [col, col+F) of sample s's latent gradient (fp32 row-major or fp16 tile format).
+template <int F>
+__device__ __forceinline__ void load_dz(const GridArgs& a, int64_t s, int col, float scale, float (&d)[F]) {
+  if (a.dz16t != nullptr) {
+    const int64_t tile = s >> 7;
+    const int r = static_cast<int>(s & 127);
+    const uint8_t* tb = a.dz16t + tile * a.kz * tc::kPanelBytes;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const int c = col + f;
+      d[f] = __half2float(*reinterpret_cast<const __half*>(tb + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63))) * scale;
+    }
+  } else {
+    const float* p = a.z + s * a.ldz + col;
+#pragma unroll
+    for (int f = 0; f < F; ++f) d[f] = __ldg(p + f) * scale;
+  }
 }
 
 constexpr int kGridThreads = 256;
@@ -282,23 +302,19 @@ __global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridAr
   pos_fract(sc, y, iy, wy);
 
   const int pw = L * F2;
-  const float* dzr = a.z + s * a.ldz;
   const float scale = a.scale_ptr ? a.scale * __ldg(a.scale_ptr) : a.scale;
   float d[F2];
   const bool fine = l >= a.lvl_begin;  // coarser levels are handled by grid_scatter_coarse_kernel
   if (a.gkf[0] != nullptr && fine) {
-#pragma unroll
-    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + l * F2 + f) * scale;
+    load_dz<F2>(a, s, l * F2, scale, d);
     plane_scatter<F2>(a.gkf[0], off, res, ix, wx, iy, wy, d);
   }
   if (a.gkf[1] != nullptr && fine) {
-#pragma unroll
-    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + l * F2 + f) * scale;
+    load_dz<F2>(a, s, pw + l * F2, scale, d);
     plane_scatter<F2>(a.gkf[1], off, res, it, wt, iy, wy, d);
   }
   if (a.gkf[2] != nullptr && fine) {
-#pragma unroll
-    for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + l * F2 + f) * scale;
+    load_dz<F2>(a, s, 2 * pw + l * F2, scale, d);
     plane_scatter<F2>(a.gkf[2], off, res, it, wt, ix, wx, d);
   }
   if (a.gsparse != nullptr) {
@@ -308,8 +324,7 @@ __global__ void __launch_bounds__(kGridThreads) grid_scatter_kernel(const GridAr
       const int cx = min(max(vx + di, 0), a.xres - 1), cy = min(max(vy + dj, 0), a.yres - 1);
       const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
       float dv[F3];
-#pragma unroll
-      for (int f = 0; f < F3; ++f) dv[f] = __ldg(dzr + 3 * pw + v * F3 + f) * scale;
+      load_dz<F3>(a, s, 3 * pw + v * F3, scale, dv);
       red_feat<F3>(a.gsparse + vox * F3, dv);
     }
   }
@@ -373,21 +388,17 @@ __global__ void __launch_bounds__(kCoarseThreads) grid_scatter_coarse_kernel(con
       pos_fract(sc, t, it, wt);
       pos_fract(sc, x, ix, wx);
       pos_fract(sc, y, iy, wy);
-      const float* dzr = a.z + s * a.ldz + l * F2;
       float d[F2];
       if (a.gkf[0] != nullptr) {
-#pragma unroll
-        for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + f) * scale;
+        load_dz<F2>(a, s, l * F2, scale, d);
         plane_scatter_smem<F2>(s_tab, off, res, ix, wx, iy, wy, d);
       }
       if (a.gkf[1] != nullptr) {
-#pragma unroll
-        for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + pw + f) * scale;
+        load_dz<F2>(a, s, pw + l * F2, scale, d);
         plane_scatter_smem<F2>(s_tab + plane_floats, off, res, it, wt, iy, wy, d);
       }
       if (a.gkf[2] != nullptr) {
-#pragma unroll
-        for (int f = 0; f < F2; ++f) d[f] = __ldg(dzr + 2 * pw + f) * scale;
+        load_dz<F2>(a, s, 2 * pw + l * F2, scale, d);
         plane_scatter_smem<F2>(s_tab + 2 * plane_floats, off, res, it, wt, ix, wx, d);
       }
     }
@@ -464,7 +475,8 @@ int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params*
 }
 
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, const float* dz,
-                        int lddz, float scale, const float* scale_ptr, const nvp_grads* g, cudaStream_t st) {
+                        int lddz, const uint8_t* dz16t, int kz, float scale, const float* scale_ptr, const nvp_grads* g,
+                        cudaStream_t st) {
   if (!g->kf_xy && !g->kf_yt && !g->kf_xt && !g->sparse) return 0;
   GridArgs a{};
   a.tab = tab;
@@ -473,6 +485,7 @@ int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coo
   a.gkf[0] = g->kf_xy; a.gkf[1] = g->kf_yt; a.gkf[2] = g->kf_xt;
   a.gsparse = g->sparse;
   a.z = const_cast<float*>(dz); a.ldz = lddz;
+  a.dz16t = dz16t; a.kz = kz;
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
   a.scale = scale;
   a.scale_ptr = scale_ptr;

@@ -419,7 +419,7 @@ int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, co
     NVP_LAUNCH_CHECK();
     if ((rc = linear_wgrad(w.dM, w.z, w.ldz, Z, g->mod_w[0], Z, m, st))) return rc;
     if ((rc = linear_dgrad(w.dM, p->mod_w[0], Z, Z, 1, w.dZ, w.ldz, m, st))) return rc;
-    if ((rc = launch_grid_scatter(d, tab, coords + 3 * s0, m, w.dZ, w.ldz, 1.0f, nullptr, g, st))) return rc;
+    if ((rc = launch_grid_scatter(d, tab, coords + 3 * s0, m, w.dZ, w.ldz, nullptr, 0, 1.0f, nullptr, g, st))) return rc;
   }
   return 0;
 }

@@ -398,14 +398,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
 //   S1  da0 = dsp1 Ws1 ; dh0 = dm1 W1h ; dz += dm1 W1z
 //   P0  dsp0 = da0*h0*cos0*w0 ; dm0 = (dh0 + da0*sin0)*lrelu'(h0)
 //   S0  dz += dm0 W0z
-//   PZ  dz -> HBM (fp32, still scaled by gs; the grid scatter un-scales)
-// The pre-activation gradient tiles dm0..2, dsp1..2 go to HBM in the MMA tile format for the wgrad
-// kernel.  The small reductions over samples (dWl, db_siren, dw/db of SIREN layer 0) are "skinny"
-// MN-major MMAs  acc[128 features, 16] += X^T R  against a per-row panel R = [drgb | 1 | 1 | 1,tau]
+//   PZ  dz -> HBM (fp16 MMA tile format, still scaled by gs; the grid scatter un-scales)
+// Data movement is all TMA: each P-phase works on one 64-column panel whose stashed activations
+// (h, sin, cos) were bulk-loaded into a shared-memory staging set, computes IN PLACE (h -> dm,
+// cos -> dsp, sin -> a2), after which the same buffers are the K-major A operands of the dgrad GEMMs,
+// the MN-major A operands of the small reductions, and the source of the bulk stores that hand
+// dm/dsp to the wgrad kernel.  Two staging sets alternate between the two panels of a step.
+// The small reductions over samples (dWl, db_siren, dw/db of SIREN layer 0) are "skinny" MN-major MMAs
+//   acc[128 features, 16] += X^T R   against a per-row panel R = [drgb | 1 | 1 | 1,tau]
 // whose 16-column blocks select the output column, accumulated across tiles in one persistent TMEM
 // accumulator and flushed once per CTA.
 enum { DP_M0 = 0, DP_M1, DP_M2, DP_S1, DP_S2, DP_COUNT };
 constexpr int kBwdPanels = 14;
+enum { ROLE_H = 0, ROLE_S = 1, ROLE_C = 2 };
+constexpr uint32_t kSetBytes = 3 * kPanelBytes;
 
 struct BwdArgs {
   const uint8_t* wpk;
@@ -421,7 +427,7 @@ struct BwdArgs {
   const float* last_w;
   float w0;
   uint8_t* dpre;         // [tile][DP_COUNT][2 panels]
-  float* dz;             // [n_tiles*128][ZP]
+  uint8_t* dz16t;        // [tile][ZP/64 panels] fp16
   float* loss_sum;
   float* g_last_w; float* g_last_b; float* g_siren_b1; float* g_siren_b2; float* g_siren_w0; float* g_siren_b0;
   int64_t n;
@@ -429,16 +435,15 @@ struct BwdArgs {
   uint32_t stage_bytes;
 };
 
-struct BwdSmem { uint32_t sp, m, x, rp, ring, consts, bars, total; };
-__host__ __device__ inline BwdSmem bwd_smem_layout(int nstage, uint32_t stage_bytes) {
+struct BwdSmem { uint32_t sets, rp, dzst, ring, consts, bars, total; };
+__host__ __device__ inline BwdSmem bwd_smem_layout(int nstage, uint32_t stage_bytes, int ZP) {
   BwdSmem s;
   uint32_t o = 0;
-  s.sp = o; o += 2 * kPanelBytes;
-  s.m = o; o += 2 * kPanelBytes;
-  s.x = o; o += 2 * kPanelBytes;
+  s.sets = o; o += 2 * kSetBytes;
   s.rp = o; o += kPanelBytes;
+  s.dzst = o; o += (ZP / 64) * kPanelBytes;
   s.ring = o; o += nstage * stage_bytes;
-  s.consts = o; o += 5 * H * 4;   // ws0[H] bs0[H] wl[3][H]
+  s.consts = o; o += 5 * H * 4;   // ws0[H] bs0[H] (both pre-multiplied by w0) wl[3][H]
   s.bars = o; o += 64 * 8;
   s.total = o;
   return s;
@@ -460,12 +465,11 @@ __device__ __forceinline__ void load_row32(const uint8_t* panel, int r, int c0, 
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const BwdSmem L = bwd_smem_layout(a.nstage, a.stage_bytes);
-  uint8_t* spbuf = smem + L.sp;
-  uint8_t* mbuf = smem + L.m;
-  uint8_t* xbuf = smem + L.x;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const BwdSmem L = bwd_smem_layout(a.nstage, a.stage_bytes, a.ZP);
+  uint8_t* sets = smem + L.sets;
   uint8_t* rp = smem + L.rp;
+  uint8_t* dzst = smem + L.dzst;
   uint8_t* ring = smem + L.ring;
   float* s_ws0 = reinterpret_cast<float*>(smem + L.consts);
   float* s_bs0 = s_ws0 + H;
@@ -473,16 +477,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* wfull = bars;
   uint64_t* wempty = bars + 16;
-  uint64_t* acc_full = bars + 34;
-  uint64_t* epi_done = bars + 35;
+  uint64_t* ld_full = bars + 32;      // [2] stash panels landed in set p
+  uint64_t* panel_done = bars + 34;   // [2] epilogue finished panel p of the current step
+  uint64_t* kp_done = bars + 36;      // [2] MMAs reading set p have completed
+  uint64_t* acc_full = bars + 38;
   __shared__ uint32_t s_tmem;
+  auto buf = [&](int set, int role) { return sets + set * kSetBytes + role * kPanelBytes; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < H; i += kThreads) { s_ws0[i] = __ldg(a.siren_w0 + i); s_bs0[i] = __ldg(a.siren_b0 + i); }
+  for (int i = tid; i < H; i += kThreads) { s_ws0[i] = __ldg(a.siren_w0 + i) * a.w0; s_bs0[i] = __ldg(a.siren_b0 + i) * a.w0; }
   for (int i = tid; i < 3 * H; i += kThreads) s_wl[i] = __ldg(a.last_w + i);
   if (tid == 0) {
     for (int i = 0; i < a.nstage; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    mbar_init(acc_full, 1); mbar_init(epi_done, kEpiWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&panel_done[i], 1); mbar_init(&kp_done[i], 1); }
+    mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
@@ -493,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
   const uint32_t acc_da = tmem, acc_dh = tmem + 128, acc_dz = tmem + 256, acc_sk = tmem + 256 + a.ZP;
 
   if (warp == 0) {
+    // ================= TMA producer: weight ring =================
     if (lane == 0) {
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -505,84 +514,109 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
       }
     }
   } else if (warp == 1) {
+    // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc_h = umma_idesc_f16(kTile, H, false, false);
       const uint32_t idesc_z = umma_idesc_f16(kTile, a.ZP, false, false);
       const uint32_t idesc_sk = umma_idesc_f16(H, 16, true, true);
-      uint32_t g = 0, n_epi = 0;
+      uint32_t g = 0, n_step = 0;
       bool sk_started = false;
-      auto panel_gemm = [&](uint8_t* abuf_, uint32_t acc, uint32_t idesc, bool accumulate) {
-        for (int q = 0; q < 2; ++q, ++g) {
-          const uint32_t st = g % a.nstage, ph = (g / a.nstage) & 1;
-          mbar_wait(&wfull[st], ph);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(abuf_ + q * kPanelBytes), b_addr = smem_u32(ring + st * a.stage_bytes);
+      auto gemm = [&](uint8_t* a_panel, uint32_t acc, uint32_t idesc, bool accumulate) {
+        const uint32_t st = g % a.nstage, ph = (g / a.nstage) & 1;
+        mbar_wait(&wfull[st], ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(a_panel), b_addr = smem_u32(ring + st * a.stage_bytes);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_f16_ss(acc, umma_desc_kmajor(a_addr, kk), umma_desc_kmajor(b_addr, kk), idesc, accumulate ? 1u : 0u);
-            accumulate = true;
-          }
-          umma_commit(&wempty[st]);
+        for (int kk = 0; kk < 4; ++kk) {
+          umma_f16_ss(acc, umma_desc_kmajor(a_addr, kk), umma_desc_kmajor(b_addr, kk), idesc, accumulate ? 1u : 0u);
+          accumulate = true;
         }
+        umma_commit(&wempty[st]);
+        ++g;
       };
-      auto skinny = [&](uint8_t* xb, int block) {
-        const uint32_t a_addr = smem_u32(xb), b_addr = smem_u32(rp) + static_cast<uint32_t>(block) * 32u;
+      auto skinny = [&](int role, int block) {   // A = role buffers of set 0 (features 0-63) and set 1 (64-127)
+        const uint32_t a_addr = smem_u32(buf(0, role)), b_addr = smem_u32(rp) + static_cast<uint32_t>(block) * 32u;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          umma_f16_ss(acc_sk, umma_desc_mnmajor(a_addr, kk, kPanelBytes), umma_desc_mnmajor(b_addr, kk, kPanelBytes),
-                      idesc_sk, sk_started ? 1u : 0u);
+          umma_f16_ss(acc_sk, umma_desc_mnmajor(a_addr, kk, kSetBytes), umma_desc_mnmajor(b_addr, kk, kPanelBytes), idesc_sk,
+                      sk_started ? 1u : 0u);
           sk_started = true;
         }
       };
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        // ---- step 2
-        mbar_wait(epi_done, n_epi & 1); ++n_epi;
-        tcgen05_fence_after();
-        panel_gemm(spbuf, acc_da, idesc_h, false);
-        panel_gemm(mbuf, acc_dh, idesc_h, false);
-        panel_gemm(mbuf, acc_dz, idesc_z, false);
-        skinny(xbuf, 0);
-        skinny(spbuf, 1);
-        umma_commit(acc_full);
-        // ---- step 1
-        mbar_wait(epi_done, n_epi & 1); ++n_epi;
-        tcgen05_fence_after();
-        panel_gemm(spbuf, acc_da, idesc_h, false);
-        panel_gemm(mbuf, acc_dh, idesc_h, false);
-        panel_gemm(mbuf, acc_dz, idesc_z, true);
-        skinny(spbuf, 2);
-        umma_commit(acc_full);
-        // ---- step 0
-        mbar_wait(epi_done, n_epi & 1); ++n_epi;
-        tcgen05_fence_after();
-        panel_gemm(mbuf, acc_dz, idesc_z, true);
-        skinny(spbuf, 3);
-        umma_commit(acc_full);
+        for (int step = 2; step >= 0; --step, ++n_step) {
+          const uint32_t par = n_step & 1;
+          // K panel 0 of dz may start as soon as panel 0 of dm is ready.  The da/dh GEMMs overwrite accumulators
+          // whose upper 64 columns the epilogue is still reading during its panel-1 phase (no TMEM left to
+          // double-buffer them), so they wait for panel 1.
+          mbar_wait(&panel_done[0], par);
+          tcgen05_fence_after();
+          gemm(buf(0, ROLE_H), acc_dz, idesc_z, step != 2);
+          mbar_wait(&panel_done[1], par);
+          tcgen05_fence_after();
+          if (step == 2) { skinny(ROLE_S, 0); skinny(ROLE_C, 1); }
+          else if (step == 1) skinny(ROLE_C, 2);
+          else skinny(ROLE_C, 3);
+          if (step > 0) {
+            gemm(buf(0, ROLE_C), acc_da, idesc_h, false);
+            gemm(buf(0, ROLE_H), acc_dh, idesc_h, false);
+          }
+          umma_commit(&kp_done[0]);
+          if (step > 0) {
+            gemm(buf(1, ROLE_C), acc_da, idesc_h, true);
+            gemm(buf(1, ROLE_H), acc_dh, idesc_h, true);
+          }
+          gemm(buf(1, ROLE_H), acc_dz, idesc_z, true);
+          umma_commit(&kp_done[1]);
+          umma_commit(acc_full);
+        }
       }
     }
   } else {
+    // ================= epilogue warps =================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
+    const int pc = sub * 32;               // my 32 columns inside the current 64-column panel
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool issuer = (tid == 64);
     const float gs = __ldg(a.gscale), inv_gs = __ldg(a.gscale + 1), loss_mult = __ldg(a.gscale + 2);
-    uint32_t n_acc = 0;
     float loss_acc = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    uint32_t n_phase[2] = {0, 0};   // completed uses of set 0 / set 1 (parity of ld_full / kp_done)
+    uint32_t n_acc = 0;
     bool any = false;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+
+    // stash panels needed by phase (step, p), bulk-loaded into staging set p
+    auto issue_loads = [&](int tile, int step, int p) {
+      const uint8_t* st_base = a.stash + (static_cast<size_t>(tile) * SL_COUNT) * 2 * kPanelBytes;
+      auto src = [&](int slot) { return st_base + (static_cast<size_t>(slot) * 2 + p) * kPanelBytes; };
+      if (step == 2) {
+        mbar_arrive_expect_tx(&ld_full[p], 3 * kPanelBytes);
+        bulk_g2s(buf(p, ROLE_H), src(SL_H2), kPanelBytes, &ld_full[p]);
+        bulk_g2s(buf(p, ROLE_S), src(SL_S2), kPanelBytes, &ld_full[p]);
+        bulk_g2s(buf(p, ROLE_C), src(SL_C2), kPanelBytes, &ld_full[p]);
+      } else if (step == 1) {
+        mbar_arrive_expect_tx(&ld_full[p], 3 * kPanelBytes);
+        bulk_g2s(buf(p, ROLE_H), src(SL_H1), kPanelBytes, &ld_full[p]);
+        bulk_g2s(buf(p, ROLE_S), src(SL_S1), kPanelBytes, &ld_full[p]);
+        bulk_g2s(buf(p, ROLE_C), src(SL_C1), kPanelBytes, &ld_full[p]);
+      } else {
+        mbar_arrive_expect_tx(&ld_full[p], kPanelBytes);
+        bulk_g2s(buf(p, ROLE_H), src(SL_H0), kPanelBytes, &ld_full[p]);
+      }
+    };
+    const int first_tile = blockIdx.x;
+    if (issuer && first_tile < a.n_tiles) { issue_loads(first_tile, 2, 0); issue_loads(first_tile, 2, 1); }
+
+    for (int tile = first_tile; tile < a.n_tiles; tile += gridDim.x) {
       any = true;
+      const int next_tile = tile + gridDim.x;
       const int64_t s = static_cast<int64_t>(tile) * kTile + r;
       const bool valid = s < a.n;
       const float tau = valid ? __ldg(a.tau + s) : 0.0f;
-      const uint8_t* st_base = a.stash + (static_cast<size_t>(tile) * SL_COUNT) * 2 * kPanelBytes;
       uint8_t* dp_base = a.dpre + (static_cast<size_t>(tile) * DP_COUNT) * 2 * kPanelBytes;
-      auto stash_ptr = [&](int slot) { return st_base + (static_cast<size_t>(slot) * 2 + half) * kPanelBytes; };
-      auto dpre_ptr = [&](int slot) { return dp_base + (static_cast<size_t>(slot) * 2 + half) * kPanelBytes; };
-      uint8_t* sp_panel = spbuf + half * kPanelBytes;
-      uint8_t* m_panel = mbuf + half * kPanelBytes;
-      uint8_t* x_panel = xbuf + half * kPanelBytes;
 
-      // ---------------- P2 ----------------
+      // drgb of my row (scaled by gs) and the per-row panel R of the small reductions
       float d0 = 0.f, d1 = 0.f, d2 = 0.f;
       if (valid) {
         if (a.dout != nullptr) {
@@ -591,11 +625,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
           const float e0 = a.rgb[s * 3] - (static_cast<float>(a.gt[s * 3]) - 127.5f) / 127.5f;
           const float e1 = a.rgb[s * 3 + 1] - (static_cast<float>(a.gt[s * 3 + 1]) - 127.5f) / 127.5f;
           const float e2 = a.rgb[s * 3 + 2] - (static_cast<float>(a.gt[s * 3 + 2]) - 127.5f) / 127.5f;
-          if (half == 0) loss_acc += e0 * e0 + e1 * e1 + e2 * e2;
+          if (sub == 0) loss_acc += e0 * e0 + e1 * e1 + e2 * e2;
           d0 = e0 * loss_mult; d1 = e1 * loss_mult; d2 = e2 * loss_mult;
         }
       }
-      if (half == 0) {
+      if (sub == 0) {
         b0 += d0; b1 += d1; b2 += d2;
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 0)) = make_uint4(pack_half2(d0, d1), pack_half2(d2, 0.f), 0u, 0u);
@@ -607,92 +641,119 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
         *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 6)) = make_uint4(0u, 0u, pack_half2(0.f, 1.f), pack_half2(tau, 0.f));
         *reinterpret_cast<uint4*>(rp + panel_chunk_offset(r, 7)) = zero;
       }
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int pc = cc * 32, col = half * 64 + pc;
-        float hv[32], sv[32], cv[32], o[32];
-        load_row32(stash_ptr(SL_H2), r, pc, hv);
-        load_row32(stash_ptr(SL_S2), r, pc, sv);
-        load_row32(stash_ptr(SL_C2), r, pc, cv);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = sv[i] * hv[i];
-        store_row32(x_panel, r, pc, o);
-        float da[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) da[i] = d0 * s_wl[col + i] + d1 * s_wl[H + col + i] + d2 * s_wl[2 * H + col + i];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = da[i] * hv[i] * cv[i];
-        store_row32(sp_panel, r, pc, o);
-        store_row32(dpre_ptr(DP_S2), r, pc, o);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = da[i] * sv[i] * (hv[i] > 0.f ? 1.f : 0.01f);
-        store_row32(m_panel, r, pc, o);
-        store_row32(dpre_ptr(DP_M2), r, pc, o);
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(epi_done);
 
-      // ---------------- P1, P0 ----------------
 #pragma unroll 1
-      for (int layer = 1; layer >= 0; --layer) {
-        mbar_wait(acc_full, n_acc & 1); ++n_acc;
-        tcgen05_fence_after();
+      for (int step = 2; step >= 0; --step) {
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int pc = cc * 32, col = half * 64 + pc;
-          uint32_t va[32], vh[32];
-          tmem_ld32(acc_da + lane_base + col, va);
-          tmem_ld32(acc_dh + lane_base + col, vh);
-          float hv[32], sv[32], cv[32], o[32];
-          load_row32(stash_ptr(layer == 1 ? SL_H1 : SL_H0), r, pc, hv);
-          float post = 1.0f;
-          if (layer == 1) {
-            load_row32(stash_ptr(SL_S1), r, pc, sv);
-            load_row32(stash_ptr(SL_C1), r, pc, cv);
-          } else {
-            post = a.w0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) fast_sincos(a.w0 * fmaf(tau, s_ws0[col + i], s_bs0[col + i]), sv[i], cv[i]);
+        for (int p = 0; p < 2; ++p) {
+          const int col = p * 64 + pc;
+          uint8_t* bh = buf(p, ROLE_H);
+          uint8_t* bs = buf(p, ROLE_S);
+          uint8_t* bc = buf(p, ROLE_C);
+          if (p == 0 && step < 2) {
+            // da/dh of this layer are complete; the MMAs that read staging set 1 are done as well
+            mbar_wait(acc_full, n_acc & 1); ++n_acc;
+            tcgen05_fence_after();
+            if (issuer) {
+              bulk_wait_read0();                       // set 1's dm/dsp bulk stores have left shared memory
+              issue_loads(tile, step, 1);
+            }
           }
-          tmem_ld_wait();
+          mbar_wait(&ld_full[p], n_phase[p] & 1);
+          float hv[32], sv[32], cv[32], o[32];
+          load_row32(bh, r, pc, hv);
+          if (step == 2) {
+            load_row32(bs, r, pc, sv);
+            load_row32(bc, r, pc, cv);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(va[i]) * hv[i] * cv[i] * post;
-          store_row32(sp_panel, r, pc, o);
-          if (layer == 1) store_row32(dpre_ptr(DP_S1), r, pc, o);
+            for (int i = 0; i < 32; ++i) o[i] = sv[i] * hv[i];     // a2, operand of the dWl reduction
+            store_row32(bs, r, pc, o);
+            float da[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            o[i] = (__uint_as_float(vh[i]) + __uint_as_float(va[i]) * sv[i]) * (hv[i] > 0.f ? 1.f : 0.01f);
-          store_row32(m_panel, r, pc, o);
-          store_row32(dpre_ptr(layer == 1 ? DP_M1 : DP_M0), r, pc, o);
+            for (int i = 0; i < 32; ++i) da[i] = d0 * s_wl[col + i] + d1 * s_wl[H + col + i] + d2 * s_wl[2 * H + col + i];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = da[i] * hv[i] * cv[i];
+            store_row32(bc, r, pc, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = da[i] * sv[i] * (hv[i] > 0.f ? 1.f : 0.01f);
+            store_row32(bh, r, pc, o);
+          } else {
+            uint32_t va[32], vh[32];
+            tmem_ld32(acc_da + lane_base + col, va);
+            tmem_ld32(acc_dh + lane_base + col, vh);
+            float post = 1.0f;
+            if (step == 1) {
+              load_row32(bs, r, pc, sv);
+              load_row32(bc, r, pc, cv);
+            } else {
+              post = a.w0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) fast_sincos(fmaf(tau, s_ws0[col + i], s_bs0[col + i]), sv[i], cv[i]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(va[i]) * hv[i] * cv[i] * post;
+            store_row32(bc, r, pc, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              o[i] = (__uint_as_float(vh[i]) + __uint_as_float(va[i]) * sv[i]) * (hv[i] > 0.f ? 1.f : 0.01f);
+            store_row32(bh, r, pc, o);
+          }
+          ++n_phase[p];
+          fence_proxy_async_smem();
+          tcgen05_fence_before();
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (issuer) {
+            auto put = [&](int slot, const uint8_t* src) {
+              bulk_s2g(dp_base + (static_cast<size_t>(slot) * 2 + p) * kPanelBytes, src, kPanelBytes);
+            };
+            if (step == 2) { put(DP_S2, bc); put(DP_M2, bh); }
+            else if (step == 1) { put(DP_S1, bc); put(DP_M1, bh); }
+            else put(DP_M0, bh);
+            bulk_commit();
+            mbar_arrive(&panel_done[p]);
+            if (p == 1) {
+              // staging set 0 is free once the small reductions (the last MMAs reading it) have completed and its
+              // bulk stores have been read: refill it for the next phase that uses it.
+              const bool more = step > 0 || next_tile < a.n_tiles;
+              if (more) {
+                mbar_wait(&kp_done[0], (n_phase[0] - 1) & 1);
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (step > 0) issue_loads(tile, step - 1, 0); else issue_loads(next_tile, 2, 0);
+              }
+            }
+          }
         }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(epi_done);
       }
 
       // ---------------- PZ ----------------
       mbar_wait(acc_full, n_acc & 1); ++n_acc;
       tcgen05_fence_after();
-      const int zh = a.ZP >> 1;
-      for (int c0 = 0; c0 < zh; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(acc_dz + lane_base + half * zh + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(a.dz + s * a.ZP + half * zh + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                 __uint_as_float(v[4 * j + 3]));
-        }
+      if (issuer && next_tile < a.n_tiles) {
+        bulk_wait_read0();
+        issue_loads(next_tile, 2, 1);
       }
+      const int zp_panels = a.ZP >> 6;
+      for (int q = 0; q < zp_panels; ++q) {
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(acc_dz + lane_base + q * 64 + pc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        store_row32(dzst + q * kPanelBytes, r, pc, f);
+      }
+      fence_proxy_async_smem();
       tcgen05_fence_before();
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (issuer) {
+        bulk_s2g(a.dz16t + static_cast<size_t>(tile) * zp_panels * kPanelBytes, dzst, zp_panels * kPanelBytes);
+        bulk_commit();
+      }
     }
+    if (issuer) bulk_wait_all0();
     // ---------------- flush of the per-CTA reductions ----------------
-    if (any && half == 0) {
+    if (any && sub == 0) {
       tcgen05_fence_after();
       uint32_t v[32];
       tmem_ld32(acc_sk + lane_base, v);
@@ -904,24 +965,26 @@ __global__ void gscale_from_absmax_kernel(const unsigned int* mx, float* g) {
   g[0] = gs; g[1] = 1.0f / gs; g[2] = 0.f;
 }
 
-// Backward weight stream per tile: [Ws2^T][W2h^T][W2z^T] [Ws1^T][W1h^T][W1z^T] [W0z^T], each as two 64-wide
-// K panels (K = output features) of a [N = input features, 128] matrix.
+// Backward weight stream per tile, in MMA consumption order: for layer 2 then 1:
+// [W_z^T 0][Ws^T 0][W_h^T 0][Ws^T 1][W_h^T 1][W_z^T 1]; then [W0z^T 0][W0z^T 1].  A K panel holds 64 output features of a
+// [N = input features, 128] matrix.
 int pack_backward_panels(const nvp_desc* d, const nvp_params* p, PackArgs& a, uint32_t base_off, BwdArgs* b) {
   const Dims m = make_dims(d);
   uint32_t off = base_off;
   int k = 0;
-  auto add = [&](const float* src, int ld, int r0, int rvalid, int rows) {
-    for (int q = 0; q < 2; ++q) {
-      b->poff[k] = off - base_off; b->pbytes[k] = static_cast<uint32_t>(rows) * 128u; ++k;
-      add_panel(a, src, ld, 1, r0, 64 * q, rvalid, 64, rows, off);
-    }
+  auto add = [&](const float* src, int ld, int r0, int rvalid, int rows, int q) {
+    b->poff[k] = off - base_off; b->pbytes[k] = static_cast<uint32_t>(rows) * 128u; ++k;
+    add_panel(a, src, ld, 1, r0, 64 * q, rvalid, 64, rows, off);
   };
   for (int i = 2; i >= 1; --i) {
-    add(p->siren_w[i], H, 0, H, H);
-    add(p->mod_w[i], H + m.Z, 0, H, H);
-    add(p->mod_w[i], H + m.Z, H, m.Z, m.ZP);
+    add(p->mod_w[i], H + m.Z, H, m.Z, m.ZP, 0);
+    for (int q = 0; q < 2; ++q) {
+      add(p->siren_w[i], H, 0, H, H, q);
+      add(p->mod_w[i], H + m.Z, 0, H, H, q);
+    }
+    add(p->mod_w[i], H + m.Z, H, m.Z, m.ZP, 1);
   }
-  add(p->mod_w[0], m.Z, 0, m.Z, m.ZP);
+  for (int q = 0; q < 2; ++q) add(p->mod_w[0], m.Z, 0, m.Z, m.ZP, q);
   return 0;
 }
 
@@ -931,7 +994,7 @@ struct TcWorkspace {
   uint8_t* z16t;
   uint8_t* stash;
   uint8_t* dpre;
-  float* dz;
+  uint8_t* dz16t;
   float* rgb;
   float* gscale;
   size_t total;
@@ -953,7 +1016,7 @@ TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
   if (what == 1) {
     w.stash = take(static_cast<size_t>(tiles) * SL_COUNT * 2 * kPanelBytes);
     w.dpre = take(static_cast<size_t>(tiles) * DP_COUNT * 2 * kPanelBytes);
-    w.dz = reinterpret_cast<float*>(take(static_cast<size_t>(tiles) * kTile * m.ZP * sizeof(float)));
+    w.dz16t = take(static_cast<size_t>(tiles) * m.KZ * kPanelBytes);
     w.gscale = reinterpret_cast<float*>(take(64));
   }
   w.total = off + 1024;
@@ -1054,17 +1117,17 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   // 5. fused backward
   b.wpk = w.wpk_bwd; b.stash = w.stash; b.tau = tsteps; b.rgb = rgb; b.gt = gt_u8; b.dout = dout; b.gscale = w.gscale;
   b.siren_w0 = p->siren_w[0]; b.siren_b0 = p->siren_b[0]; b.last_w = p->last_w; b.w0 = d->w0_first;
-  b.dpre = w.dpre; b.dz = w.dz; b.loss_sum = loss_sum;
+  b.dpre = w.dpre; b.dz16t = w.dz16t; b.loss_sum = loss_sum;
   b.g_last_w = g->last_w; b.g_last_b = g->last_b; b.g_siren_b1 = g->siren_b[1]; b.g_siren_b2 = g->siren_b[2];
   b.g_siren_w0 = g->siren_w[0]; b.g_siren_b0 = g->siren_b[0];
   b.n = n; b.n_tiles = n_tiles; b.ZP = m.ZP;
   b.stage_bytes = static_cast<uint32_t>(m.ZP) * 128u;
   b.nstage = 0;
   for (int ns = 12; ns >= 2; --ns)
-    if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes).total) <= kSmemBudget) { b.nstage = ns; break; }
+    if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes, m.ZP).total) <= kSmemBudget) { b.nstage = ns; break; }
   NVP_CHECK(b.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core backward");
   {
-    const size_t smem = bwd_smem_layout(b.nstage, b.stage_bytes).total + 1024;
+    const size_t smem = bwd_smem_layout(b.nstage, b.stage_bytes, m.ZP).total + 1024;
     NVP_CUDA(cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ScopedKernelTimer timer(K_MLP_BWD, st);
     mlp_backward_kernel<<<std::min(n_tiles, num_sms()), kThreads, smem, st>>>(b);
@@ -1090,7 +1153,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   }
 
   // 7. scatter-add into the grids (dz is still multiplied by gs)
-  return launch_grid_scatter(d, tab, coords, n, w.dz, m.ZP, 1.0f, w.gscale + 1, g, st);
+  return launch_grid_scatter(d, tab, coords, n, nullptr, 0, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, st);
 }
 
 }  // namespace nvp
