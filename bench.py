@@ -67,19 +67,6 @@ def synth_batch(n: int, seed: int):
     return coords.contiguous(), tsteps.contiguous(), torch.stack(chans, dim=1).contiguous()
 
 
-def attach_flat_grads(model):
-    """All gradients as views into ONE flat fp32 buffer (single memset, single NCCL all-reduce)."""
-    ps = [p for p in model.parameters() if p.requires_grad]
-    offs, total = [], 0
-    for p in ps:
-        offs.append(total)
-        total += (p.numel() + 63) // 64 * 64
-    flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
-    for p, o in zip(ps, offs):
-        p.grad = flat[o:o + p.numel()].view_as(p)
-    return flat
-
-
 class ClockSampler:
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
@@ -211,6 +198,7 @@ def run_ours(args):
     import torch.distributed as dist
     import nvp_b200
     from nvp_b200 import _lib, functional
+    from nvp_b200.dist import attach_flat_grads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -1,0 +1,89 @@
+"""Coordinate sampler and video container — host code kept from the reference (dataio.py:11-120).
+
+Same classes, same tensors, same torch-RNG consumption (two `torch.randint` calls per batch, t first), so
+a seeded run draws exactly the reference's sample stream.  `.mp4` input needs scikit-video (absent in this
+image) and is gated; `.npy` and PNG directories work.
+"""
+import glob
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+
+def get_mgrid(sidelen, dim=2):
+    """Flattened grid of coordinates in [0, 1] (dataio.py:11-29)."""
+    if isinstance(sidelen, int):
+        sidelen = dim * (sidelen,)
+    if dim == 2:
+        pixel_coords = np.stack(np.mgrid[:sidelen[0], :sidelen[1]], axis=-1)[None, ...].astype(np.float32)
+        pixel_coords[0, :, :, 0] = pixel_coords[0, :, :, 0] / (sidelen[0] - 1)
+        pixel_coords[0, :, :, 1] = pixel_coords[0, :, :, 1] / (sidelen[1] - 1)
+    elif dim == 3:
+        pixel_coords = np.stack(np.mgrid[:sidelen[0], :sidelen[1], :sidelen[2]], axis=-1)[None, ...].astype(np.float32)
+        pixel_coords[..., 0] = pixel_coords[..., 0] / max(sidelen[0] - 1, 1)
+        pixel_coords[..., 1] = pixel_coords[..., 1] / (sidelen[1] - 1)
+        pixel_coords[..., 2] = pixel_coords[..., 2] / (sidelen[2] - 1)
+    else:
+        raise NotImplementedError('Not implemented for dim=%d' % dim)
+    return torch.Tensor(pixel_coords).view(-1, dim)
+
+
+class VideoTime(Dataset):
+    """uint8 video [T,H,W,3] from a .npy file, an in-memory array, or a directory of PNGs (dataio.py:33-71)."""
+
+    def __init__(self, path_to_video, split_num=300):
+        super().__init__()
+        self.split_num = split_num
+        if isinstance(path_to_video, np.ndarray):
+            self.vid = path_to_video
+        elif 'npy' in path_to_video:
+            self.vid = np.load(path_to_video)
+        elif 'mp4' in path_to_video:
+            raise NotImplementedError("mp4 input needs scikit-video, which is not installed; convert to .npy or PNGs")
+        else:
+            from PIL import Image
+            files = sorted(glob.glob(os.path.join(path_to_video, "*.png")))[:self.split_num]
+            first = np.array(Image.open(files[0]))
+            self.vid = np.zeros((self.split_num,) + first.shape, dtype=np.uint8)
+            for idx, f in enumerate(files):
+                self.vid[idx] = np.array(Image.open(f))
+        self.shape = self.vid.shape[1:-1]
+        self.nframes = self.vid.shape[0]
+        self.channels = self.vid.shape[-1]
+
+    def __len__(self):
+        return 1
+
+    def __getitem__(self, idx):
+        return self.vid
+
+
+class VideoTimeWrapper(torch.utils.data.Dataset):
+    """Random (t, pixel) sampler, N_samples per item (dataio.py:75-120)."""
+
+    def __init__(self, dataset, sidelength=None, n_samples=1245184):
+        self.dataset = dataset
+        nframes = self.dataset.nframes
+        self.sidelength = sidelength
+        self.mgrid = get_mgrid(sidelength, dim=2)
+        data = torch.from_numpy(self.dataset[0])
+        self.data = data.view(self.dataset.nframes, -1, self.dataset.channels)
+        self.N_samples = n_samples
+        half_dt = 0.5 / nframes
+        self.temporal_steps = torch.linspace(half_dt, 1 - half_dt, self.dataset.nframes)
+        self.temporal_coords = torch.linspace(0, 1, nframes)
+
+    def __len__(self):
+        return len(self.dataset)
+
+    def __getitem__(self, idx):
+        temporal_coord_idx = torch.randint(0, self.data.shape[0], (self.N_samples,))
+        spatial_coord_idx = torch.randint(0, self.data.shape[1], (self.N_samples,))
+        data = self.data[temporal_coord_idx, spatial_coord_idx, :]
+        spatial_coords = self.mgrid[spatial_coord_idx, :]
+        temporal_coords = self.temporal_coords[temporal_coord_idx]
+        temporal_steps = self.temporal_steps[temporal_coord_idx]
+        all_coords = torch.cat((temporal_coords.unsqueeze(1), spatial_coords), dim=1)
+        return {'all_coords': all_coords, "temporal_steps": temporal_steps}, {'img': data}

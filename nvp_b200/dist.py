@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: one process per GPU, coordinate batches sharded across ranks, ONE
+all-reduce (sum) of a flat fp32 gradient buffer per step.  The reference has no distributed code; this is the
+data-parallel scheme the north star asks for.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the
+only communication layer; the kernels take `n_global` so each shard's gradients are already scaled for the
+global mean and a plain sum reproduces the single-GPU gradient.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, near-equal split of n samples; the first n % world ranks take one extra."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def attach_flat_grads(model: torch.nn.Module, align: int = 64) -> torch.Tensor:
+    """Make every parameter's .grad a view into one zero-filled flat buffer (offsets aligned to `align` floats so
+    vector reductions stay 16-byte aligned).  Returns the flat buffer: zero it once per step, all-reduce it once."""
+    ps = [p for p in model.parameters() if p.requires_grad]
+    offs, total = [], 0
+    for p in ps:
+        offs.append(total)
+        total += (p.numel() + align - 1) // align * align
+    flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+    for p, o in zip(ps, offs):
+        p.grad = flat[o:o + p.numel()].view_as(p)
+    return flat
+
+
+def all_reduce_grads(flat: torch.Tensor, group=None) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0, group=None) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, src, group=group)
+
+
+class ShardedStep:
+    """Runs the fused step on this rank's shard of a GLOBAL batch that every rank holds (or can slice).
+
+    step(model_input, gt_u8): inputs are the global batch [1, N, ...]; the rank processes samples
+    shard_range(N, rank, world), accumulates into the flat gradient buffer and all-reduces it (and the loss sum).
+    """
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+        self.flat = attach_flat_grads(model)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.loss_sum: Optional[torch.Tensor] = None
+
+    def step(self, model_input: Dict[str, torch.Tensor], gt_u8: torch.Tensor) -> torch.Tensor:
+        coords = model_input["all_coords"].reshape(-1, 3)
+        tsteps = model_input["temporal_steps"].reshape(-1)
+        gt = gt_u8.reshape(-1, 3)
+        n = coords.shape[0]
+        lo, hi = shard_range(n, self.rank, self.world)
+        if self.loss_sum is None:
+            self.loss_sum = torch.zeros(1, dtype=torch.float32, device=coords.device)
+        self.flat.zero_()
+        self.loss_sum.zero_()
+        if hi > lo:
+            self.model.fwd_loss_bwd({"all_coords": coords[lo:hi], "temporal_steps": tsteps[lo:hi]}, gt[lo:hi],
+                                    n_global=n, loss_sum=self.loss_sum)
+        all_reduce_grads(self.flat, self.group)
+        all_reduce_grads(self.loss_sum, self.group)
+        return self.loss_sum / (3.0 * n)

@@ -1,0 +1,109 @@
+"""CPU tests of the kept host code (sampler, training glue) and of the multi-GPU plumbing (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nvp_b200 import dataio
+from nvp_b200.dist import attach_flat_grads, shard_range
+from oracle import check_vs_reference as R
+from oracle import nvp_oracle as O
+
+
+def test_sampler_matches_oracle_and_reference_stream():
+    T, H, W, n = 5, 12, 16, 1000
+    vid = O.synthetic_video(T, H, W, seed=1)
+    ds = dataio.VideoTime(vid)
+    w = dataio.VideoTimeWrapper(ds, sidelength=ds.shape, n_samples=n)
+    torch.manual_seed(7)
+    a, b = w[0]
+    torch.manual_seed(7)
+    c, ts, img = O.sample_batch(torch.from_numpy(vid).view(T, -1, 3), O.get_mgrid_2d(H, W), n)
+    assert torch.equal(a["all_coords"], c) and torch.equal(a["temporal_steps"], ts) and torch.equal(b["img"], img)
+    assert a["all_coords"].dtype == torch.float32 and b["img"].dtype == torch.uint8
+    assert w.N_samples == n and dataio.VideoTimeWrapper(ds, sidelength=ds.shape).N_samples == 1245184  # dataio.py:91
+    if R.reference_available():
+        ref = R.import_reference()
+
+        class DS:
+            nframes, channels, shape = T, 3, (H, W)
+
+            def __len__(self):
+                return 1
+
+            def __getitem__(self, i):
+                return vid
+
+        rw = ref.dataio.VideoTimeWrapper(DS(), sidelength=(H, W))
+        rw.N_samples = n
+        torch.manual_seed(7)
+        ra, rb = rw[0]
+        assert torch.equal(ra["all_coords"], a["all_coords"]) and torch.equal(rb["img"], b["img"])
+        assert torch.equal(ref.dataio.get_mgrid((H, W), 2), dataio.get_mgrid((H, W), 2))
+
+
+@pytest.mark.parametrize("n,world", [(1245184, 8), (10, 4), (3, 8), (0, 2), (1000, 3)])
+def test_shard_ranges_partition_the_batch(n, world):
+    spans = [shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a, b), (c, d) in zip(spans, spans[1:]):
+        assert b == c and a <= b and c <= d
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_flat_gradient_buffer_aliases_param_grads():
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    flat = attach_flat_grads(m)
+    assert flat.numel() % 64 == 0
+    for p in m.parameters():
+        assert p.grad.data_ptr() >= flat.data_ptr() and (p.grad.data_ptr() - flat.data_ptr()) % 256 == 0
+        p.grad.add_(1.0)
+    assert float(flat.sum()) == sum(p.numel() for p in m.parameters())
+    flat.zero_()
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in m.parameters())
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nvp_b200.dist import all_reduce_grads, broadcast_parameters
+    torch.manual_seed(rank)  # different init per rank -> broadcast must equalise
+    m = torch.nn.Linear(6, 4)
+    broadcast_parameters(m, 0)
+    flat = attach_flat_grads(m)
+    # emulate the sharded step on CPU: each rank contributes the gradient of ITS shard of a global batch with the
+    # global-mean scaling (what the kernels do with n_global), then one all-reduce
+    g = torch.Generator().manual_seed(123)
+    x, y = torch.randn(10, 6, generator=g), torch.randn(10, 4, generator=g)
+    lo, hi = shard_range(10, rank, world)
+    loss = ((m(x[lo:hi]) - y[lo:hi]) ** 2).sum() / (10 * 4)
+    gw, gb = torch.autograd.grad(loss, [m.weight, m.bias])
+    m.weight.grad.add_(gw)
+    m.bias.grad.add_(gb)
+    all_reduce_grads(flat)
+    full = ((m(x) - y) ** 2).mean()
+    fw, fb = torch.autograd.grad(full, [m.weight, m.bias])
+    ok = torch.allclose(m.weight.grad, fw, atol=1e-6) and torch.allclose(m.bias.grad, fb, atol=1e-6)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shards_sum_to_the_global_gradient():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
