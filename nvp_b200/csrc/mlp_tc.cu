@@ -13,6 +13,7 @@
 // shared memory, so all global->shared traffic is plain bulk TMA and the same stored activation tile
 // serves the forward, dgrad (K-major) and wgrad (MN-major) GEMMs.
 #include <algorithm>
+#include <initializer_list>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -160,7 +161,8 @@ struct FwdArgs {
 struct FwdSmem {  // offsets into dynamic smem (1024-B aligned base)
   uint32_t z, h, a, s, c, ring, consts, rgbx, bars, total;
 };
-__host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage, bool train) {
+__host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage, bool stage_sc) {
+  const bool train = stage_sc;
   FwdSmem s;
   uint32_t o = 0;
   s.z = o; o += KZ * kPanelBytes;
@@ -183,11 +185,13 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage, bool trai
 //     memory the MMA warp issues the K-panel-p GEMMs of step i+1.
 //   * Train mode: every stashed activation tile is staged in shared memory in the MMA tile format and
 //     leaves through cp.async.bulk (TMA) stores, one 16 KiB panel at a time.
-template <bool TRAIN>
+// STAGE_SC: stage the sin/cos stash tiles in shared memory for TMA bulk stores (needs 64 KiB); when the latent is too
+// wide for that (config L) they are written with per-lane 16-byte stores instead.
+template <bool TRAIN, bool STAGE_SC>
 __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const FwdSmem L = fwd_smem_layout(a.KZ, a.nstage, TRAIN);
+  const FwdSmem L = fwd_smem_layout(a.KZ, a.nstage, TRAIN && STAGE_SC);
   uint8_t* zbuf = smem + L.z;
   uint8_t* hbuf = smem + L.h;
   uint8_t* abuf = smem + L.a;
@@ -340,9 +344,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
               if (TRAIN) fast_sincos(sp, sv[i], cv[i]); else sv[i] = fast_sin(sp);
               av[i] = sv[i] * hv[i];
             }
-            if (TRAIN) {
+            if (TRAIN && STAGE_SC) {
               store_row32(sbuf + p * kPanelBytes, r, pc, sv);
               store_row32(cbuf + p * kPanelBytes, r, pc, cv);
+            } else if (TRAIN) {
+              store_row32(st_base + (static_cast<size_t>(step == 1 ? SL_S1 : SL_S2) * 2 + p) * kPanelBytes, r, pc, sv);
+              store_row32(st_base + (static_cast<size_t>(step == 1 ? SL_C1 : SL_C2) * 2 + p) * kPanelBytes, r, pc, cv);
             }
           }
           if (step < 2 || TRAIN) store_row32(hbuf + p * kPanelBytes, r, pc, hv);
@@ -366,8 +373,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
                 bulk_s2g(st_base + (static_cast<size_t>(slot) * 2 + p) * kPanelBytes, src + p * kPanelBytes, kPanelBytes);
               };
               if (step == 0) { put(SL_H0, hbuf); put(SL_A0, abuf); }
-              else if (step == 1) { put(SL_H1, hbuf); put(SL_A1, abuf); put(SL_S1, sbuf); put(SL_C1, cbuf); }
-              else { put(SL_H2, hbuf); put(SL_S2, sbuf); put(SL_C2, cbuf); }
+              else if (step == 1) { put(SL_H1, hbuf); put(SL_A1, abuf); if (STAGE_SC) { put(SL_S1, sbuf); put(SL_C1, cbuf); } }
+              else { put(SL_H2, hbuf); if (STAGE_SC) { put(SL_S2, sbuf); put(SL_C2, cbuf); } }
               bulk_commit();
             }
             mbar_arrive(&panel_done[step * 2 + p]);
@@ -431,17 +438,18 @@ struct BwdArgs {
   float* loss_sum;
   float* g_last_w; float* g_last_b; float* g_siren_b1; float* g_siren_b2; float* g_siren_w0; float* g_siren_b0;
   int64_t n;
-  int n_tiles, ZP, nstage;
+  int n_tiles, ZP, NZ, nstage;   // NZ = dz GEMM width = round_up(Z+1, 16) <= ZP
+  int stage_dz;                  // 1: dz tiles staged in smem and bulk-stored; 0: per-lane stores (no smem left)
   uint32_t stage_bytes;
 };
 
 struct BwdSmem { uint32_t sets, rp, dzst, ring, consts, bars, total; };
-__host__ __device__ inline BwdSmem bwd_smem_layout(int nstage, uint32_t stage_bytes, int ZP) {
+__host__ __device__ inline BwdSmem bwd_smem_layout(int nstage, uint32_t stage_bytes, int ZP, int stage_dz) {
   BwdSmem s;
   uint32_t o = 0;
   s.sets = o; o += 2 * kSetBytes;
   s.rp = o; o += kPanelBytes;
-  s.dzst = o; o += (ZP / 64) * kPanelBytes;
+  s.dzst = o; if (stage_dz) o += (ZP / 64) * kPanelBytes;
   s.ring = o; o += nstage * stage_bytes;
   s.consts = o; o += 5 * H * 4;   // ws0[H] bs0[H] (both pre-multiplied by w0) wl[3][H]
   s.bars = o; o += 64 * 8;
@@ -466,7 +474,7 @@ __device__ __forceinline__ void load_row32(const uint8_t* panel, int r, int c0, 
 __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const BwdSmem L = bwd_smem_layout(a.nstage, a.stage_bytes, a.ZP);
+  const BwdSmem L = bwd_smem_layout(a.nstage, a.stage_bytes, a.ZP, a.stage_dz);
   uint8_t* sets = smem + L.sets;
   uint8_t* rp = smem + L.rp;
   uint8_t* dzst = smem + L.dzst;
@@ -498,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t acc_da = tmem, acc_dh = tmem + 128, acc_dz = tmem + 256, acc_sk = tmem + 256 + a.ZP;
+  const uint32_t acc_da = tmem, acc_dh = tmem + 128, acc_dz = tmem + 256, acc_sk = tmem + 256 + a.NZ;
 
   if (warp == 0) {
     // ================= TMA producer: weight ring =================
@@ -517,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc_h = umma_idesc_f16(kTile, H, false, false);
-      const uint32_t idesc_z = umma_idesc_f16(kTile, a.ZP, false, false);
+      const uint32_t idesc_z = umma_idesc_f16(kTile, a.NZ, false, false);
       const uint32_t idesc_sk = umma_idesc_f16(H, 16, true, true);
       uint32_t g = 0, n_step = 0;
       bool sk_started = false;
@@ -734,20 +742,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
         issue_loads(next_tile, 2, 1);
       }
       const int zp_panels = a.ZP >> 6;
+      uint8_t* dz_tile = a.dz16t + static_cast<size_t>(tile) * zp_panels * kPanelBytes;
       for (int q = 0; q < zp_panels; ++q) {
+        if (q * 64 + pc >= a.NZ) break;        // columns >= NZ hold no gradient (never read by the scatter)
         uint32_t v[32];
         float f[32];
         tmem_ld32(acc_dz + lane_base + q * 64 + pc, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        store_row32(dzst + q * kPanelBytes, r, pc, f);
+        store_row32((a.stage_dz ? dzst : dz_tile) + q * kPanelBytes, r, pc, f);
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      if (issuer) {
-        bulk_s2g(a.dz16t + static_cast<size_t>(tile) * zp_panels * kPanelBytes, dzst, zp_panels * kPanelBytes);
+      if (issuer && a.stage_dz) {
+        bulk_s2g(dz_tile, dzst, zp_panels * kPanelBytes);
         bulk_commit();
       }
     }
@@ -755,8 +765,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
     // ---------------- flush of the per-CTA reductions ----------------
     if (any && sub == 0) {
       tcgen05_fence_after();
-      uint32_t v[32];
-      tmem_ld32(acc_sk + lane_base, v);
+      uint32_t v[16];
+      tmem_ld16(acc_sk + lane_base, v);
       tmem_ld_wait();
       const int j = r;  // feature index
       if (a.g_last_w) {
@@ -801,6 +811,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
 constexpr int kWgThreads = 192;
 constexpr int kHalfPanelBytes = kPanelBytes / 2;  // 64 rows
 
+// Operand sources: 0..DP_COUNT-1 = dpre slot, 16+slot = stash slot, 64 = latent z.
+enum { WG_SRC_STASH = 16, WG_SRC_Z = 64 };
+// Gradient targets of a product.
+enum { WG_W0Z = 0, WG_W1H, WG_W1Z, WG_W2H, WG_W2Z, WG_WS1, WG_WS2 };
+
+struct WgProduct { int a_hp, b_hp, is_z, tmem_col, target; };   // operand positions in half-panels inside a stage
+struct WgKind {
+  int n_ops, op_src[6], n_hp;   // operands loaded per stage and total half-panels
+  int n_prod;
+  WgProduct prod[4];
+  int cta_begin, cta_end;
+};
 struct WgArgs {
   const uint8_t* dpre;
   const uint8_t* stash;
@@ -811,22 +833,22 @@ struct WgArgs {
   float* g_siren_w[3];
   int n_units;   // half tiles
   int KZ, Z, ZP;
-  int n_a;       // CTAs [0, n_a) are kind A
+  int n_kinds;
+  WgKind kind[3];
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full[2], empty[2], done;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool kindA = static_cast<int>(blockIdx.x) < a.n_a;
-  const int rank = kindA ? blockIdx.x : blockIdx.x - a.n_a;
-  const int stride = kindA ? a.n_a : static_cast<int>(gridDim.x) - a.n_a;
-  // operand slots inside a stage (in half-panels of 8 KiB):
-  //   kind A: dm1[2] dsp1[2] h0[2] a0[2] z[KZ]        kind B: dm0[2] dm2[2] dsp2[2] h1[2] a1[2] z[KZ]
-  const int n_half_panels = (kindA ? 8 : 10) + a.KZ;
-  const uint32_t stage_bytes = static_cast<uint32_t>(n_half_panels) * kHalfPanelBytes;
+  int ki = 0;
+  while (ki + 1 < a.n_kinds && static_cast<int>(blockIdx.x) >= a.kind[ki].cta_end) ++ki;
+  const WgKind& K = a.kind[ki];
+  const int rank = blockIdx.x - K.cta_begin;
+  const int stride = K.cta_end - K.cta_begin;
+  const uint32_t stage_bytes = static_cast<uint32_t>(K.n_hp) * kHalfPanelBytes;
 
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1); mbar_init(&done, 1);
@@ -852,17 +874,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgArgs a
         const uint8_t* dp = a.dpre + static_cast<size_t>(tile) * DP_COUNT * 2 * kPanelBytes;
         const uint8_t* sb = a.stash + static_cast<size_t>(tile) * SL_COUNT * 2 * kPanelBytes;
         const uint8_t* zt = a.z16t + static_cast<size_t>(tile) * a.KZ * kPanelBytes;
-        auto two = [&](const uint8_t* base, int slot) {
-          for (int q = 0; q < 2; ++q) {
-            bulk_g2s(dst, base + (static_cast<size_t>(slot) * 2 + q) * kPanelBytes + hoff, kHalfPanelBytes, &full[st]);
+        for (int o = 0; o < K.n_ops; ++o) {
+          const int src = K.op_src[o];
+          const uint8_t* base = src == WG_SRC_Z ? zt : (src >= WG_SRC_STASH ? sb + static_cast<size_t>(src - WG_SRC_STASH) * 2 * kPanelBytes
+                                                                           : dp + static_cast<size_t>(src) * 2 * kPanelBytes);
+          const int np = src == WG_SRC_Z ? a.KZ : 2;
+          for (int q = 0; q < np; ++q) {
+            bulk_g2s(dst, base + static_cast<size_t>(q) * kPanelBytes + hoff, kHalfPanelBytes, &full[st]);
             dst += kHalfPanelBytes;
           }
-        };
-        if (kindA) { two(dp, DP_M1); two(dp, DP_S1); two(sb, SL_H0); two(sb, SL_A0); }
-        else { two(dp, DP_M0); two(dp, DP_M2); two(dp, DP_S2); two(sb, SL_H1); two(sb, SL_A1); }
-        for (int q = 0; q < a.KZ; ++q) {
-          bulk_g2s(dst, zt + static_cast<size_t>(q) * kPanelBytes + hoff, kHalfPanelBytes, &full[st]);
-          dst += kHalfPanelBytes;
         }
       }
     }
@@ -876,22 +896,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgArgs a
         mbar_wait(&full[st], ph);
         tcgen05_fence_after();
         const uint32_t sb = smem_u32(smem + st * stage_bytes);
-        auto hp = [&](int i) { return sb + static_cast<uint32_t>(i) * kHalfPanelBytes; };
-        auto prod = [&](uint32_t acc, int a_slot, int b_slot, uint32_t idesc) {
+        for (int pi = 0; pi < K.n_prod; ++pi) {
+          const WgProduct& P = K.prod[pi];
+          const uint32_t a_addr = sb + static_cast<uint32_t>(P.a_hp) * kHalfPanelBytes;
+          const uint32_t b_addr = sb + static_cast<uint32_t>(P.b_hp) * kHalfPanelBytes;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16_ss(acc, umma_desc_mnmajor(hp(a_slot), kk, kHalfPanelBytes), umma_desc_mnmajor(hp(b_slot), kk, kHalfPanelBytes),
-                        idesc, (it > 0 || kk > 0) ? 1u : 0u);
-        };
-        if (kindA) {
-          prod(tmem + 0, 0, 4, idesc_h);            // dW1h = dm1^T h0
-          prod(tmem + 128, 0, 8, idesc_z);          // dW1z = dm1^T z
-          prod(tmem + 128 + a.ZP, 2, 6, idesc_h);   // dWs1 = dsp1^T a0
-        } else {
-          prod(tmem + 0, 0, 10, idesc_z);                   // dW0z = dm0^T z
-          prod(tmem + a.ZP, 2, 6, idesc_h);                 // dW2h = dm2^T h1
-          prod(tmem + a.ZP + 128, 2, 10, idesc_z);          // dW2z = dm2^T z
-          prod(tmem + 2 * a.ZP + 128, 4, 8, idesc_h);       // dWs2 = dsp2^T a1
+            umma_f16_ss(tmem + P.tmem_col, umma_desc_mnmajor(a_addr, kk, kHalfPanelBytes),
+                        umma_desc_mnmajor(b_addr, kk, kHalfPanelBytes), P.is_z ? idesc_z : idesc_h, (it > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty[st]);
       }
@@ -905,44 +917,73 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgArgs a
     const int j = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const float inv_gs = __ldg(a.gscale + 1);
-    auto flush_h = [&](uint32_t acc, float* g, int ld, int col_off) {
-      if (g == nullptr) return;
-      for (int c0 = 0; c0 < H; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(acc + lane_base + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(g + static_cast<size_t>(j) * ld + col_off + c0 + i, __uint_as_float(v[i]) * inv_gs);
+    for (int pi = 0; pi < K.n_prod; ++pi) {
+      const WgProduct& P = K.prod[pi];
+      float* gw; float* gb = nullptr; int ld, col_off = 0;
+      switch (P.target) {
+        case WG_W0Z: gw = a.g_mod_w[0]; gb = a.g_mod_b[0]; ld = a.Z; break;
+        case WG_W1H: gw = a.g_mod_w[1]; ld = H + a.Z; break;
+        case WG_W1Z: gw = a.g_mod_w[1]; gb = a.g_mod_b[1]; ld = H + a.Z; col_off = H; break;
+        case WG_W2H: gw = a.g_mod_w[2]; ld = H + a.Z; break;
+        case WG_W2Z: gw = a.g_mod_w[2]; gb = a.g_mod_b[2]; ld = H + a.Z; col_off = H; break;
+        case WG_WS1: gw = a.g_siren_w[1]; ld = H; break;
+        default:     gw = a.g_siren_w[2]; ld = H; break;
       }
-    };
-    auto flush_z = [&](uint32_t acc, float* gw, int ld, int col_off, float* gb) {
-      for (int c0 = 0; c0 < a.ZP; c0 += 32) {
-        if (c0 > a.Z) break;
+      const int ncol = P.is_z ? a.Z + 1 : H;   // column Z of a z product = sum of dm over samples = bias gradient
+      for (int c0 = 0; c0 < ncol; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(acc + lane_base + c0, v);
+        tmem_ld32(tmem + P.tmem_col + lane_base + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c = c0 + i;
-          if (c < a.Z) { if (gw) atomicAdd(gw + static_cast<size_t>(j) * ld + col_off + c, __uint_as_float(v[i]) * inv_gs); }
-          else if (c == a.Z) { if (gb) atomicAdd(gb + j, __uint_as_float(v[i]) * inv_gs); }
+          const float val = __uint_as_float(v[i]) * inv_gs;
+          if (!P.is_z || c < a.Z) { if (gw) atomicAdd(gw + static_cast<size_t>(j) * ld + col_off + c, val); }
+          else if (c == a.Z) { if (gb) atomicAdd(gb + j, val); }
         }
       }
-    };
-    if (kindA) {
-      flush_h(tmem + 0, a.g_mod_w[1], H + a.Z, 0);
-      flush_z(tmem + 128, a.g_mod_w[1], H + a.Z, H, a.g_mod_b[1]);
-      flush_h(tmem + 128 + a.ZP, a.g_siren_w[1], H, 0);
-    } else {
-      flush_z(tmem + 0, a.g_mod_w[0], a.Z, 0, a.g_mod_b[0]);
-      flush_h(tmem + a.ZP, a.g_mod_w[2], H + a.Z, 0);
-      flush_z(tmem + a.ZP + 128, a.g_mod_w[2], H + a.Z, H, a.g_mod_b[2]);
-      flush_h(tmem + 2 * a.ZP + 128, a.g_siren_w[2], H, 0);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// Host-side plan: which products each CTA kind keeps resident in its 512 TMEM columns.
+void build_wgrad_plan(WgArgs& wa, int sms) {
+  const int ZP = wa.ZP, KZ = wa.KZ;
+  auto kind = [&](std::initializer_list<int> srcs, std::initializer_list<WgProduct> prods) {
+    WgKind k{};
+    int hp = 0;
+    for (int src : srcs) { k.op_src[k.n_ops++] = src; hp += (src == WG_SRC_Z ? KZ : 2); }
+    k.n_hp = hp;
+    int col = 0;
+    for (WgProduct p : prods) { p.tmem_col = col; col += p.is_z ? ZP : H; k.prod[k.n_prod++] = p; }
+    return k;
+  };
+  // operand half-panel positions follow the order of `srcs`: each dpre/stash operand takes 2, z takes KZ.
+  const WgKind A = kind({DP_M1, DP_S1, WG_SRC_STASH + SL_H0, WG_SRC_STASH + SL_A0, WG_SRC_Z},
+                        {{0, 4, 0, 0, WG_W1H}, {0, 8, 1, 0, WG_W1Z}, {2, 6, 0, 0, WG_WS1}});
+  if (2 * ZP + 256 <= 512) {
+    const WgKind B = kind({DP_M0, DP_M2, DP_S2, WG_SRC_STASH + SL_H1, WG_SRC_STASH + SL_A1, WG_SRC_Z},
+                          {{0, 10, 1, 0, WG_W0Z}, {2, 6, 0, 0, WG_W2H}, {2, 10, 1, 0, WG_W2Z}, {4, 8, 0, 0, WG_WS2}});
+    wa.n_kinds = 2; wa.kind[0] = A; wa.kind[1] = B;
+  } else {
+    const WgKind B = kind({DP_M2, DP_S2, WG_SRC_STASH + SL_H1, WG_SRC_STASH + SL_A1, WG_SRC_Z},
+                          {{0, 4, 0, 0, WG_W2H}, {0, 8, 1, 0, WG_W2Z}, {2, 6, 0, 0, WG_WS2}});
+    const WgKind C = kind({DP_M0, WG_SRC_Z}, {{0, 2, 1, 0, WG_W0Z}});
+    wa.n_kinds = 3; wa.kind[0] = A; wa.kind[1] = B; wa.kind[2] = C;
+  }
+  // CTAs per kind proportional to the bytes a kind streams per unit (every kind sweeps all units)
+  int total_hp = 0;
+  for (int k = 0; k < wa.n_kinds; ++k) total_hp += wa.kind[k].n_hp;
+  int begin = 0, left = sms;
+  for (int k = 0; k < wa.n_kinds; ++k) {
+    int c = (k == wa.n_kinds - 1) ? left : std::max(1, sms * wa.kind[k].n_hp / total_hp);
+    c = std::max(1, std::min(c, wa.n_units));
+    wa.kind[k].cta_begin = begin; wa.kind[k].cta_end = begin + c;
+    begin += c; left -= c;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1045,20 +1086,27 @@ int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w,
   a.w0 = d->w0_first; a.rgb = rgb; a.stash = w.stash; a.n = n;
   a.n_tiles = static_cast<int>((n + kTile - 1) / kTile);
   a.KZ = m.KZ; a.npf = m.npf;
+  bool stage_sc = train;
   a.nstage = 0;
-  for (int ns = 12; ns >= 2; --ns)
-    if (static_cast<int>(fwd_smem_layout(m.KZ, ns, train).total) <= kSmemBudget) { a.nstage = ns; break; }
+  for (int pass = 0; pass < 2 && a.nstage == 0; ++pass) {
+    for (int ns = 12; ns >= 2; --ns)
+      if (static_cast<int>(fwd_smem_layout(m.KZ, ns, stage_sc).total) <= kSmemBudget) { a.nstage = ns; break; }
+    if (a.nstage == 0) stage_sc = false;
+  }
   NVP_CHECK(a.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core path");
-  const size_t smem = fwd_smem_layout(m.KZ, a.nstage, train).total + 1024;
+  const size_t smem = fwd_smem_layout(m.KZ, a.nstage, stage_sc).total + 1024;
   const int grid = std::min(a.n_tiles, num_sms());
   ScopedKernelTimer timer(K_MLP_FWD, st);
-  if (train) {
-    NVP_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    mlp_forward_kernel<true><<<grid, kThreads, smem, st>>>(a);
-  } else {
-    NVP_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    mlp_forward_kernel<false><<<grid, kThreads, smem, st>>>(a);
-  }
+  auto launch = [&](auto kernel) -> int {
+    NVP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<grid, kThreads, smem, st>>>(a);
+    return 0;
+  };
+  int rc;
+  if (!train) rc = launch(mlp_forward_kernel<false, false>);
+  else if (stage_sc) rc = launch(mlp_forward_kernel<true, true>);
+  else rc = launch(mlp_forward_kernel<true, false>);
+  if (rc) return rc;
   NVP_LAUNCH_CHECK();
   return 0;
 }
@@ -1084,7 +1132,8 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
                float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st) {
   NVP_CHECK(ws_bytes >= tc_workspace_bytes(d, n, 1), "workspace too small (see nvp_workspace_bytes)");
   const Dims m = make_dims(d);
-  NVP_CHECK(2 * m.ZP + 256 <= 512, "tensor-core backward: latent wider than 127 columns (config L) is not built yet");
+  const int NZ = round_up(m.Z + 1, 16);
+  NVP_CHECK(m.ZP <= 256 && 256 + NZ + 16 <= 512, "tensor-core backward: latent wider than 239 columns is not built");
   void* base = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
   const TcWorkspace w = carve_tc(d, n, 1, base);
   const int n_tiles = static_cast<int>((n + kTile - 1) / kTile);
@@ -1120,14 +1169,17 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   b.dpre = w.dpre; b.dz16t = w.dz16t; b.loss_sum = loss_sum;
   b.g_last_w = g->last_w; b.g_last_b = g->last_b; b.g_siren_b1 = g->siren_b[1]; b.g_siren_b2 = g->siren_b[2];
   b.g_siren_w0 = g->siren_w[0]; b.g_siren_b0 = g->siren_b[0];
-  b.n = n; b.n_tiles = n_tiles; b.ZP = m.ZP;
+  b.n = n; b.n_tiles = n_tiles; b.ZP = m.ZP; b.NZ = NZ;
   b.stage_bytes = static_cast<uint32_t>(m.ZP) * 128u;
   b.nstage = 0;
-  for (int ns = 12; ns >= 2; --ns)
-    if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes, m.ZP).total) <= kSmemBudget) { b.nstage = ns; break; }
+  for (b.stage_dz = 1; b.stage_dz >= 0 && b.nstage == 0; --b.stage_dz) {
+    for (int ns = 12; ns >= 3; --ns)
+      if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes, m.ZP, b.stage_dz).total) <= kSmemBudget) { b.nstage = ns; break; }
+    if (b.nstage) break;
+  }
   NVP_CHECK(b.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core backward");
   {
-    const size_t smem = bwd_smem_layout(b.nstage, b.stage_bytes, m.ZP).total + 1024;
+    const size_t smem = bwd_smem_layout(b.nstage, b.stage_bytes, m.ZP, b.stage_dz).total + 1024;
     NVP_CUDA(cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ScopedKernelTimer timer(K_MLP_BWD, st);
     mlp_backward_kernel<<<std::min(n_tiles, num_sms()), kThreads, smem, st>>>(b);
@@ -1140,15 +1192,14 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
     wa.dpre = w.dpre; wa.stash = w.stash; wa.z16t = w.z16t; wa.gscale = w.gscale;
     for (int i = 0; i < 3; ++i) { wa.g_mod_w[i] = g->mod_w[i]; wa.g_mod_b[i] = g->mod_b[i]; wa.g_siren_w[i] = g->siren_w[i]; }
     wa.n_units = 2 * n_tiles; wa.KZ = m.KZ; wa.Z = m.Z; wa.ZP = m.ZP;
-    const int sms = num_sms();
-    int na = std::max(1, std::min(wa.n_units, (sms * 45) / 100));
-    int nb = std::max(1, std::min(wa.n_units, sms - na));
-    wa.n_a = na;
-    const size_t smem = 2 * static_cast<size_t>(10 + m.KZ) * kHalfPanelBytes + 1024;
-    NVP_CHECK(static_cast<int>(smem) <= kSmemBudget + 1024, "latent too wide for the wgrad shared-memory plan");
+    build_wgrad_plan(wa, num_sms());
+    int max_hp = 0;
+    for (int k = 0; k < wa.n_kinds; ++k) max_hp = std::max(max_hp, wa.kind[k].n_hp);
+    const size_t smem = 2 * static_cast<size_t>(max_hp) * kHalfPanelBytes + 1024;
+    NVP_CHECK(static_cast<int>(smem) <= kSmemBudget + 1024 && m.ZP + 256 <= 512, "latent too wide for the wgrad plan");
     NVP_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ScopedKernelTimer timer(K_MLP_WGRAD, st);
-    mlp_wgrad_kernel<<<na + nb, kWgThreads, smem, st>>>(wa);
+    mlp_wgrad_kernel<<<wa.kind[wa.n_kinds - 1].cta_end, kWgThreads, smem, st>>>(wa);
     NVP_LAUNCH_CHECK();
   }
 
