@@ -47,12 +47,14 @@ def load_config(name: str) -> dict:
         return json.load(f)["nvp"]
 
 
-def synth_batch(n: int, seed: int):
+def synth_batch(n: int, seed: int, t_range=None):
     """One sampler batch (dataio.py:104-120) over a virtual synthetic video: the pixel value is a smooth
-    pattern plus hash noise evaluated at the sampled (t,row,col) — the 3.7 GB video is never materialised."""
+    pattern plus hash noise evaluated at the sampled (t,row,col) — the 3.7 GB video is never materialised.
+    t_range=(lo,hi) restricts the frame index to a rank's t-slab (stratified version of the uniform sampler)."""
     T, Hh, Ww = VIDEO
     g = torch.Generator().manual_seed(seed)
-    t_idx = torch.randint(0, T, (n,), generator=g)
+    lo, hi = t_range if t_range is not None else (0, T)
+    t_idx = torch.randint(lo, hi, (n,), generator=g)
     p_idx = torch.randint(0, Hh * Ww, (n,), generator=g)
     row, col = p_idx // Ww, p_idx % Ww
     coords = torch.stack((torch.linspace(0, 1, T)[t_idx], row.float() / (Hh - 1), col.float() / (Ww - 1)), dim=1)
@@ -188,7 +190,9 @@ def bench_config(args, mode):
                         f"{N_SAMPLES} sampled coordinates per step per GPU",
             "nvp_config": f"config_nvp_{args.config}", "samples_per_step_per_gpu": N_SAMPLES, "mode": mode,
             "step": "grad-buffer zero + gather + fused MLP fwd + L2 loss + fused bwd + wgrad + grid scatter"
-                    + (" + NCCL all-reduce of the flat gradient buffer" if args.gpus > 1 else ""),
+                    + ((" + NCCL all-reduce of the whole flat gradient buffer" if args.full_allreduce else
+                        " + NCCL all-reduce of keyframe+MLP gradients (sparse 3-D grid owned per rank by t-slab, samples "
+                        "stratified by slab)") if args.gpus > 1 else ""),
             "l2": "working set >> L2 (543 MB params + 543 MB grads + 4.6 GB activation tiles per step); 8 rotating input batches",
             "parallelism": f"dp{args.gpus}"}
 
@@ -217,14 +221,23 @@ def run_ours(args):
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, 0)
-    flat = attach_flat_grads(model)
+    # t-slab ownership of the sparse grid: its gradient sits at the end of the flat buffer and is
+    # excluded from the all-reduce; every rank samples frames of its own slab only.
+    slab = world > 1 and not args.full_allreduce
+    flat = attach_flat_grads(model, last=[model.sparse_grid.embeddings] if slab else ())
+    reduce_view = flat[:flat.replicated_numel] if slab else flat
+    t_range = None
+    if slab:
+        from nvp_b200.dist import t_slab
+        t_range = t_slab(cfg_json["3d_encoding"]["t_resolution"], rank, world)
+        assert cfg_json["3d_encoding"]["t_resolution"] == VIDEO[0]
     n, n_global = N_SAMPLES, N_SAMPLES * world
     F = cfg_json["2d_encoding_xy"]["n_features_per_level"]
 
     n_pool = 8
     host = []
     for i in range(n_pool):
-        c, t, g = synth_batch(n, 1000 * rank + i)
+        c, t, g = synth_batch(n, 1000 * rank + i, t_range)
         host.append((c.pin_memory(), t.pin_memory(), g.pin_memory()))
     resident = [(c.to(dev), t.to(dev), g.to(dev)) for c, t, g in host]
     stage = (torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1]), torch.empty_like(resident[0][2]))
@@ -237,7 +250,7 @@ def run_ours(args):
         model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum)
         launches[0] += functional.last_launch_count()
         if world > 1:
-            dist.all_reduce(flat)
+            dist.all_reduce(reduce_view)
 
     def barrier():
         torch.cuda.synchronize()
@@ -351,6 +364,7 @@ def main():
     ap.add_argument("--config", default="s", choices=["s", "l"])
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-allreduce", action="store_true", help="N>1: all-reduce the whole gradient (no t-slab ownership)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -19,10 +19,13 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def attach_flat_grads(model: torch.nn.Module, align: int = 64) -> torch.Tensor:
+def attach_flat_grads(model: torch.nn.Module, align: int = 64, last=()) -> torch.Tensor:
     """Make every parameter's .grad a view into one zero-filled flat buffer (offsets aligned to `align` floats so
-    vector reductions stay 16-byte aligned).  Returns the flat buffer: zero it once per step, all-reduce it once."""
-    ps = [p for p in model.parameters() if p.requires_grad]
+    vector reductions stay 16-byte aligned).  Returns the flat buffer: zero it once per step, all-reduce it once.
+    Parameters listed in `last` are placed at the end of the buffer (see replicated_numel)."""
+    last_ids = {id(p) for p in last}
+    ps = [p for p in model.parameters() if p.requires_grad and id(p) not in last_ids]
+    ps += [p for p in last if p.requires_grad]
     offs, total = [], 0
     for p in ps:
         offs.append(total)
@@ -30,7 +33,15 @@ def attach_flat_grads(model: torch.nn.Module, align: int = 64) -> torch.Tensor:
     flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
     for p, o in zip(ps, offs):
         p.grad = flat[o:o + p.numel()].view_as(p)
+    flat.replicated_numel = offs[len(ps) - len([p for p in last if p.requires_grad])] if last else total
     return flat
+
+
+def t_slab(t_resolution: int, rank: int, world: int) -> Tuple[int, int]:
+    """Frames [lo, hi) of the 3-D sparse grid owned by `rank`.  SparseGrid.forward indexes the grid by the NEAREST
+    frame only (sparsegrid.py:43-46,65), so a rank whose samples all have t inside its slab reads and updates that
+    slab alone: the sparse grid (80 % of all parameters) needs no collective, only keyframes + MLP are all-reduced."""
+    return shard_range(t_resolution, rank, world)
 
 
 def all_reduce_grads(flat: torch.Tensor, group=None) -> None:
