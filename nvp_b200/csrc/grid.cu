@@ -94,7 +94,8 @@ struct GridArgs {
   const float* scale_ptr;  // optional device scalar multiplied into scale
   const uint8_t* dz16t;    // scatter input in fp16 MMA tile format (kz panels per 128-sample tile) when non-null
   int lvl_begin;           // scatter: keyframe levels [lvl_begin, L) go straight to global memory
-  int n_coarse;            // coarse kernel: levels [0, n_coarse) are privatised in shared memory
+  int n_coarse;            // coarse kernels: levels [0, n_coarse) live in shared memory
+  int n_coarse_chunks;     // gather v2: 16-byte chunks per plane handled by the coarse kernel
   int coarse_cells;        // offset[n_coarse]
   int64_t chunk;           // coarse kernel: samples per CTA
 };
@@ -440,6 +441,215 @@ int launch_coarse(const GridArgs& a, int blocks, size_t smem, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tile-format gather, v2 (used when n_levels * F2 is a multiple of 8, i.e. both reference configs).
+// A 16-byte chunk of a latent row holds LPC = 8 / F2 consecutive levels of one plane, so one thread produces one
+// whole chunk (one st.global.v4) instead of F2 halfs.
+//   * gather_coarse_kernel: persistent CTAs, one keyframe plane each; levels [0, LC) of that plane are staged in
+//     shared memory (<= 180 KB) and serve the corner reads of the first CC chunks (44 % of all corner reads for S)
+//     without touching L2.
+//   * gather_fine_kernel: blockIdx.y walks (plane, chunk) pairs for the remaining levels - the tables of one pass
+//     (<= 34 MB for S) stay L2-resident while every sample is processed - plus one pass for the 3x3 voxel
+//     neighbourhood and the padding columns.
+// ------------------------------------------------------------------------------------------
+constexpr int kCoarseGatherThreads = 1024;
+
+template <int F2>
+__device__ __forceinline__ void bilinear_any(const float* __restrict__ gtab, const float* __restrict__ stab, bool in_smem,
+                                             int off, int res, int i0, float w0, int i1, float w1, float (&acc)[F2]) {
+  const int cells = res * res;
+  const int b00 = i0 + i1 * res;
+  const int c00 = wrap_cell(b00, cells), c10 = wrap_cell(b00 + 1, cells);
+  const int c01 = wrap_cell(b00 + res, cells), c11 = wrap_cell(b00 + res + 1, cells);
+  float v00[F2], v10[F2], v01[F2], v11[F2];
+  if (in_smem) {
+    const float* base = stab + static_cast<size_t>(off) * F2;
+#pragma unroll
+    for (int f = 0; f < F2; ++f) {
+      v00[f] = base[c00 * F2 + f]; v10[f] = base[c10 * F2 + f]; v01[f] = base[c01 * F2 + f]; v11[f] = base[c11 * F2 + f];
+    }
+  } else {
+    const float* base = gtab + static_cast<size_t>(off) * F2;
+    ld_feat<F2>(base + static_cast<size_t>(c00) * F2, v00);
+    ld_feat<F2>(base + static_cast<size_t>(c10) * F2, v10);
+    ld_feat<F2>(base + static_cast<size_t>(c01) * F2, v01);
+    ld_feat<F2>(base + static_cast<size_t>(c11) * F2, v11);
+  }
+  const float a0 = 1.0f - w0, a1 = 1.0f - w1;
+  const float k00 = a0 * a1, k10 = w0 * a1, k01 = a0 * w1, k11 = w0 * w1;
+#pragma unroll
+  for (int f = 0; f < F2; ++f) {
+    float r = k00 * v00[f];
+    r = fmaf(k10, v10[f], r);
+    r = fmaf(k01, v01[f], r);
+    r = fmaf(k11, v11[f], r);
+    acc[f] = r;
+  }
+}
+
+// One 16-byte chunk (levels [chunk*LPC, chunk*LPC+LPC) of `plane`) of sample s's latent row.
+template <int F2>
+__device__ __forceinline__ void gather_chunk(const GridArgs& a, const float* s_scale, const int* s_res, const int* s_off,
+                                             const float* stab, int n_smem_levels, int plane, int chunk, int64_t s) {
+  constexpr int LPC = 8 / F2;
+  const int64_t tile = s >> 7;
+  const int r = static_cast<int>(s & 127);
+  const int col = plane * a.tab.n_levels * F2 + chunk * 8;
+  uint8_t* dst = a.z16t + (tile * a.kz + (col >> 6)) * tc::kPanelBytes + tc::panel_chunk_offset(r, (col & 63) >> 3);
+  if (s >= a.n) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
+  const float u0 = plane == 0 ? x : t;          // xy: (x, y); yt: (t, y); xt: (t, x)   modules.py:61-63
+  const float u1 = plane == 2 ? x : y;
+  float out[8];
+#pragma unroll
+  for (int j = 0; j < LPC; ++j) {
+    const int l = chunk * LPC + j;
+    int i0, i1;
+    float w0, w1;
+    pos_fract(s_scale[l], u0, i0, w0);
+    pos_fract(s_scale[l], u1, i1, w1);
+    float acc[F2];
+    bilinear_any<F2>(a.kf[plane], stab, l < n_smem_levels, s_off[l], s_res[l], i0, w0, i1, w1, acc);
+#pragma unroll
+    for (int f = 0; f < F2; ++f) out[j * F2 + f] = acc[f];
+  }
+  uint4 q;
+  q.x = tc::pack_half2(out[0], out[1]); q.y = tc::pack_half2(out[2], out[3]);
+  q.z = tc::pack_half2(out[4], out[5]); q.w = tc::pack_half2(out[6], out[7]);
+  *reinterpret_cast<uint4*>(dst) = q;
+}
+
+template <int F2>
+__global__ void __launch_bounds__(kCoarseGatherThreads) gather_coarse_kernel(const GridArgs a) {
+  extern __shared__ float s_tab[];
+  __shared__ float s_scale[NVP_MAX_LEVELS];
+  __shared__ int s_res[NVP_MAX_LEVELS];
+  __shared__ int s_off[NVP_MAX_LEVELS];
+  if (threadIdx.x < a.tab.n_levels) {
+    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
+    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
+    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
+  }
+  const int plane = blockIdx.x % 3;
+  const int rank = blockIdx.x / 3, nrank = (gridDim.x - plane + 2) / 3;   // CTAs serving this plane
+  const int nfl = a.coarse_cells * F2;
+  for (int i = threadIdx.x; i < nfl; i += kCoarseGatherThreads) s_tab[i] = __ldg(a.kf[plane] + i);
+  __syncthreads();
+  const int64_t per = (a.n_pad + nrank - 1) / nrank;
+  const int64_t s0 = rank * per, s1 = min(a.n_pad, s0 + per);
+  const int64_t items = (s1 - s0) * a.n_coarse_chunks;
+  for (int64_t i = threadIdx.x; i < items; i += kCoarseGatherThreads) {
+    const int chunk = static_cast<int>(i / (s1 - s0));
+    const int64_t s = s0 + (i - chunk * (s1 - s0));
+    gather_chunk<F2>(a, s_scale, s_res, s_off, s_tab, a.n_coarse, plane, chunk, s);
+  }
+}
+
+template <int F2, int F3>
+__global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArgs a) {
+  __shared__ float s_scale[NVP_MAX_LEVELS];
+  __shared__ int s_res[NVP_MAX_LEVELS];
+  __shared__ int s_off[NVP_MAX_LEVELS];
+  const int L = a.tab.n_levels;
+  if (threadIdx.x < L) {
+    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
+    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
+    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x;
+  if (s >= a.n_pad) return;
+  constexpr int LPC = 8 / F2;
+  const int cpp = L / LPC;                        // chunks per plane
+  const int fine_per_plane = cpp - a.n_coarse_chunks;
+  const int pass = blockIdx.y;
+  if (pass < 3 * fine_per_plane) {
+    // chunk-major so that consecutive passes reuse the same levels' working set size class; plane fastest
+    const int chunk = a.n_coarse_chunks + pass / 3, plane = pass % 3;
+    gather_chunk<F2>(a, s_scale, s_res, s_off, nullptr, 0, plane, chunk, s);
+    return;
+  }
+  // last pass: 3x3 neighbourhood of the nearest voxel + padding columns (constant 1 at column Z, then zeros),
+  // assembled in registers and written as whole 16-byte chunks (column 3*L*F2 is chunk aligned).
+  const int64_t tile = s >> 7;
+  const int r = static_cast<int>(s & 127);
+  uint8_t* tbase = a.z16t + tile * a.kz * tc::kPanelBytes;
+  const int c0 = 3 * L * F2;
+  constexpr int NV = 9 * F3;                 // voxel features
+  constexpr int NCH = (NV + 1 + 7) / 8;      // chunks holding features + the constant-1 column
+  auto chunk_ptr = [&](int c) {
+    return reinterpret_cast<uint4*>(tbase + (c >> 6) * tc::kPanelBytes + tc::panel_chunk_offset(r, (c & 63) >> 3));
+  };
+  const int total_chunks = (a.kz * 64 - c0) >> 3;
+  if (s >= a.n) {
+    for (int j = 0; j < total_chunks; ++j) *chunk_ptr(c0 + 8 * j) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
+  const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
+  float vals[NCH * 8];
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i) vals[i] = (i == NV) ? 1.0f : 0.0f;
+#pragma unroll
+  for (int v = 0; v < 9; ++v) {
+    const int di = v / 3 - 1, dj = v - (v / 3) * 3 - 1;
+    const int cx = min(max(vx + di, 0), a.xres - 1), cy = min(max(vy + dj, 0), a.yres - 1);
+    const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
+    float fv[F3];
+    ld_feat<F3>(a.sparse + vox * F3, fv);
+#pragma unroll
+    for (int f = 0; f < F3; ++f) vals[v * F3 + f] = fv[f];
+  }
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    if (j < total_chunks) {
+      uint4 q;
+      q.x = tc::pack_half2(vals[8 * j + 0], vals[8 * j + 1]); q.y = tc::pack_half2(vals[8 * j + 2], vals[8 * j + 3]);
+      q.z = tc::pack_half2(vals[8 * j + 4], vals[8 * j + 5]); q.w = tc::pack_half2(vals[8 * j + 6], vals[8 * j + 7]);
+      *chunk_ptr(c0 + 8 * j) = q;
+    }
+  }
+  for (int j = NCH; j < total_chunks; ++j) *chunk_ptr(c0 + 8 * j) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <int F2>
+int launch_gather_v2(const GridArgs& a0, int f3, cudaStream_t st) {
+  GridArgs a = a0;
+  constexpr int LPC = 8 / F2;
+  const int L = a.tab.n_levels;
+  int lc = 0;
+  while (lc < L && static_cast<size_t>(a.tab.offset[lc + 1]) * F2 * sizeof(float) <= 180 * 1024) ++lc;
+  a.n_coarse = lc;
+  a.coarse_cells = a.tab.offset[lc];
+  a.n_coarse_chunks = std::min(L / LPC, (lc + LPC - 1) / LPC);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (a.n_coarse_chunks > 0) {
+    const size_t smem = static_cast<size_t>(a.coarse_cells) * F2 * sizeof(float);
+    NVP_CUDA(cudaFuncSetAttribute(gather_coarse_kernel<F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int blocks = static_cast<int>(std::max<int64_t>(3, std::min<int64_t>(sms, (a.n_pad + 255) / 256 * 3)));
+    ScopedKernelTimer timer(K_GATHER, st);
+    gather_coarse_kernel<F2><<<blocks, kCoarseGatherThreads, smem, st>>>(a);
+    NVP_LAUNCH_CHECK();
+  }
+  const int passes = 3 * (L / LPC - a.n_coarse_chunks) + 1;
+  dim3 grid(static_cast<unsigned>((a.n_pad + kGridThreads - 1) / kGridThreads), passes);
+  ScopedKernelTimer timer(K_GATHER, st);
+  switch (f3) {
+    case 1: gather_fine_kernel<F2, 1><<<grid, kGridThreads, 0, st>>>(a); break;
+    case 2: gather_fine_kernel<F2, 2><<<grid, kGridThreads, 0, st>>>(a); break;
+    case 4: gather_fine_kernel<F2, 4><<<grid, kGridThreads, 0, st>>>(a); break;
+    case 8: gather_fine_kernel<F2, 8><<<grid, kGridThreads, 0, st>>>(a); break;
+    default: NVP_CHECK(false, "3d n_features_per_level must be 1, 2, 4 or 8");
+  }
+  NVP_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int F2, int F3>
 void launch_pair(bool scatter, const GridArgs& a, int blocks, cudaStream_t st) {
   if (scatter)
@@ -490,6 +700,14 @@ int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params*
   a.z = z; a.ldz = ldz; a.z16t = z16t; a.kz = kz; a.n_pad = (n + 127) / 128 * 128;
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
   a.scale = 1.0f;
+  if (z == nullptr && z16t != nullptr && (tab.n_levels * d->n_features) % 8 == 0 && n >= 4096) {
+    switch (d->n_features) {
+      case 1: return launch_gather_v2<1>(a, d->sparse_features, st);
+      case 2: return launch_gather_v2<2>(a, d->sparse_features, st);
+      case 4: return launch_gather_v2<4>(a, d->sparse_features, st);
+      case 8: return launch_gather_v2<8>(a, d->sparse_features, st);
+    }
+  }
   return dispatch(false, d->n_features, d->sparse_features, a, st);
 }
 
