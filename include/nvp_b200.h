@@ -131,6 +131,14 @@ int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords
 /* Number of kernels the last call on this thread enqueued (for bench.py's gpu_launches). */
 int nvp_last_launch_count(void);
 
+/* Fused AdamW step over flat fp32 buffers (reference training.py:13-14,73-76:
+ * torch.optim.AdamW(weight_decay=1e-3) + optim.zero_grad()).  `step` is the 1-based step count used for the bias
+ * corrections, `lr` the (cosine-annealed) learning rate of this step; zero_grad != 0 clears `grads` in the same pass.
+ * Buffers must be 16-byte aligned. */
+int nvp_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, int zero_grad,
+                   void* stream);
+
 /* Per-kernel device timing with CUDA events on the launch stream (bench.py's roofline leg).
  * After nvp_profile_enable(1) every kernel the library enqueues on this thread is bracketed by an
  * event pair; nvp_profile_read synchronises those events, returns per-kind totals and resets.

@@ -5,8 +5,8 @@ import bench, nvp_b200
 cfg = bench.load_config("s")
 torch.manual_seed(0)
 m = nvp_b200.NVP(out_features=3, encoding_config=cfg, mode="tc").cuda()
-from nvp_b200.dist import attach_flat_grads
-flat = attach_flat_grads(m)
+from nvp_b200.optim import flatten_parameters
+_, flat = flatten_parameters(m)
 c, t, g = [x.cuda() for x in bench.synth_batch(bench.N_SAMPLES, 0)]
 ls = torch.zeros(1, device="cuda")
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
