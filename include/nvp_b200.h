@@ -91,6 +91,9 @@ enum {
   NVP_MODE_FP32_SIMT = 0, /* fp32 FFMA on CUDA cores: bit-faithful to the reference's fp32 semantics */
   NVP_MODE_TC_F16    = 1  /* tcgen05 tensor cores, fp16 operands / fp32 accumulate in TMEM */
 };
+/* OR-ed into `mode` of nvp_forward: evaluate the 3-D grid with SparseGrid.forward_inter (sparsegrid.py:76-156,
+ * selected by NVP.forward(temporal_interp=True), modules.py:72-73; eval-only, no backward). */
+#define NVP_FLAG_TEMPORAL_INTERP 0x100
 
 int nvp_version(void);
 const char* nvp_last_error(void);
@@ -138,6 +141,17 @@ int nvp_last_launch_count(void);
 int nvp_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int64_t step, int zero_grad,
                    void* stream);
+
+/* Device-resident sampler (reference dataio.py:85-99,104-120 + the per-step host gather and
+ * H2D copy of training.py:45-48).  video: uint8 [T, H*W, 3] in device memory; temporal_coords / temporal_steps: the
+ * two [T] look-up tables of dataio.py:96,99.  Indices come either from t_idx / p_idx (int64 device arrays, e.g. the
+ * reference's CPU RNG stream uploaded: identical batches) or, when both are NULL, from Philox4x32-10 keyed by
+ * (seed, step, sample) with frames restricted to [t_lo, t_hi).  Outputs: coords [n,3], tsteps [n], gt [n,3] uint8 and
+ * optionally the drawn indices (int32). */
+int nvp_sample_batch(const uint8_t* video, int T, int H, int W, const float* temporal_coords,
+                     const float* temporal_steps, int64_t n, const int64_t* t_idx, const int64_t* p_idx,
+                     uint64_t seed, uint64_t step, int t_lo, int t_hi, float* coords, float* tsteps, uint8_t* gt,
+                     int32_t* t_idx_out, int32_t* p_idx_out, void* stream);
 
 /* Per-kernel device timing with CUDA events on the launch stream (bench.py's roofline leg).
  * After nvp_profile_enable(1) every kernel the library enqueues on this thread is bracketed by an

@@ -16,6 +16,7 @@ NVP_MAX_LEVELS = 32
 NVP_MAX_LAYERS = 3
 MODE_FP32_SIMT = 0
 MODE_TC_F16 = 1
+FLAG_TEMPORAL_INTERP = 0x100
 MODES = {"fp32": MODE_FP32_SIMT, "simt": MODE_FP32_SIMT, "tc": MODE_TC_F16, "f16": MODE_TC_F16}
 
 
@@ -41,7 +42,7 @@ class NvpPtrs(C.Structure):
 EXPORTS = (
     "nvp_version", "nvp_last_error", "nvp_level_table", "nvp_latent_dim", "nvp_workspace_bytes",
     "nvp_encode_latent", "nvp_forward", "nvp_backward", "nvp_fwd_loss_bwd", "nvp_last_launch_count",
-    "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step",
+    "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step", "nvp_sample_batch",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -69,6 +70,7 @@ def load() -> C.CDLL:
     lib.nvp_backward.argtypes = [D, P, vp, vp, vp, i64, P, vp, C.c_size_t, i32, vp]
     lib.nvp_fwd_loss_bwd.argtypes = [D, P, vp, vp, vp, i64, i64, P, vp, vp, vp, C.c_size_t, i32, vp]
     lib.nvp_adamw_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, i32, vp]
+    lib.nvp_sample_batch.argtypes = [vp, i32, i32, i32, vp, vp, i64, vp, vp, C.c_uint64, C.c_uint64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.nvp_profile_enable.argtypes = [i32]
     lib.nvp_profile_read.argtypes = [i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.nvp_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]

@@ -156,6 +156,7 @@ int nvp_workspace_bytes(const nvp_desc* d, int64_t n, int mode, int what, size_t
   if (int rc = validate_desc(d)) return rc;
   NVP_CHECK(bytes != nullptr, "bytes is NULL");
   NVP_CHECK(what == 0 || what == 1, "what must be 0 (forward) or 1 (backward)");
+  mode &= 0xff;
   if (mode == NVP_MODE_FP32_SIMT) *bytes = simt_workspace_bytes(d, n, what);
   else if (mode == NVP_MODE_TC_F16) *bytes = tc_workspace_bytes(d, n, what);
   else NVP_CHECK(false, "unknown mode");
@@ -188,8 +189,10 @@ int nvp_forward(const nvp_desc* d, const nvp_params* p, const float* coords, con
   if ((rc = check_device_ptr(out_rgb, "out_rgb"))) return rc;
   if ((rc = check_device_ptr(workspace, "workspace"))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == NVP_MODE_FP32_SIMT) return simt_forward(d, tab, p, coords, tsteps, n, out_rgb, workspace, workspace_bytes, st);
-  if (mode == NVP_MODE_TC_F16) return tc_forward(d, tab, p, coords, tsteps, n, out_rgb, workspace, workspace_bytes, st);
+  const bool interp = (mode & NVP_FLAG_TEMPORAL_INTERP) != 0;
+  mode &= 0xff;
+  if (mode == NVP_MODE_FP32_SIMT) return simt_forward(d, tab, p, coords, tsteps, n, out_rgb, workspace, workspace_bytes, st, interp);
+  if (mode == NVP_MODE_TC_F16) return tc_forward(d, tab, p, coords, tsteps, n, out_rgb, workspace, workspace_bytes, st, interp);
   NVP_CHECK(false, "unknown mode");
 }
 

@@ -72,7 +72,8 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // z (fp32 row-major, pitch ldz floats) and/or z16t (fp16 MMA tile format, kz 64-column panels per
 // 128-sample tile; see tc_common.cuh).
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
-                       int64_t n, float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st);
+                       int64_t n, float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st,
+                       bool temporal_interp = false);
 // grads += scatter of dz scaled by `scale` (times *scale_ptr when given).  dz is either fp32 row-major
 // (pitch lddz) or, when dz16t != NULL, fp16 in the MMA tile format with kz panels per 128-sample tile.
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
@@ -82,7 +83,8 @@ int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coo
 // ---- mlp_simt.cu --------------------------------------------------------------------------
 size_t simt_workspace_bytes(const nvp_desc* d, int64_t n, int what);
 int simt_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
-                 const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);
+                 const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st,
+                 bool temporal_interp = false);
 // dout == nullptr -> loss mode (gt_u8, n_global, loss_sum used); else explicit upstream gradient.
 int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
                  const float* tsteps, const uint8_t* gt_u8, const float* dout, int64_t n, int64_t n_global,
@@ -91,7 +93,8 @@ int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, co
 // ---- mlp_tc.cu ----------------------------------------------------------------------------
 size_t tc_workspace_bytes(const nvp_desc* d, int64_t n, int what);
 int tc_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
-               const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);
+               const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st,
+               bool temporal_interp = false);
 int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
                const float* tsteps, const uint8_t* gt_u8, const float* dout, int64_t n, int64_t n_global,
                const nvp_grads* g, float* loss_sum, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st);

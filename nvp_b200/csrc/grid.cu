@@ -90,6 +90,7 @@ struct GridArgs {
   int kz;              // panels per tile (ZP / 64)
   int64_t n_pad;       // rows to write (multiple of 128; rows >= n are zero-filled)
   int tres, xres, yres;
+  int interp;              // gather: SparseGrid.forward_inter (eval-time temporal blend) instead of nearest frame
   float scale;
   const float* scale_ptr;  // optional device scalar multiplied into scale
   const uint8_t* dz16t;    // scatter input in fp16 MMA tile format (kz panels per 128-sample tile) when non-null
@@ -99,6 +100,38 @@ struct GridArgs {
   int coarse_cells;        // offset[n_coarse]
   int64_t chunk;           // coarse kernel: samples per CTA
 };
+
+// Frame selection of the 3-D grid: nearest frame (sparsegrid.py:43-46) or, for temporal_interp, the blend of the
+// frames below/above with the reference's coefficient quirk (sparsegrid.py:102-109): upper is normalised first and
+// lower is then divided by (new upper + lower); 0/0 = NaN at the last frame, as in the reference.
+struct SparseTime { int t0, t1; float w0, w1; };
+__device__ __forceinline__ SparseTime sparse_time(const GridArgs& a, float t) {
+  SparseTime s;
+  if (!a.interp) {
+    s.t0 = s.t1 = nearest_voxel(t, a.tres); s.w0 = 1.0f; s.w1 = 0.0f;
+    return s;
+  }
+  const float tf = __fmul_rn(static_cast<float>(a.tres - 1), t);
+  const int lower = __float2int_rz(tf);
+  const int upper = min(max(__float2int_rz(__fadd_rn(tf, 1.0f)), 0), a.tres - 1);
+  float up = __fsub_rn(tf, static_cast<float>(lower)), lo = __fsub_rn(static_cast<float>(upper), tf);
+  up = __fdiv_rn(up, __fadd_rn(up, lo));
+  lo = __fdiv_rn(lo, __fadd_rn(up, lo));
+  s.t0 = min(max(lower, 0), a.tres - 1); s.t1 = upper; s.w0 = lo; s.w1 = up;
+  return s;
+}
+template <int F3>
+__device__ __forceinline__ void sparse_fetch(const GridArgs& a, const SparseTime& st, int cx, int cy, float (&fv)[F3]) {
+  const size_t v0 = (static_cast<size_t>(st.t0) * a.xres + cx) * a.yres + cy;
+  ld_feat<F3>(a.sparse + v0 * F3, fv);
+  if (a.interp) {
+    const size_t v1 = (static_cast<size_t>(st.t1) * a.xres + cx) * a.yres + cy;
+    float fu[F3];
+    ld_feat<F3>(a.sparse + v1 * F3, fu);
+#pragma unroll
+    for (int f = 0; f < F3; ++f) fv[f] = __fadd_rn(__fmul_rn(fv[f], st.w0), __fmul_rn(fu[f], st.w1));
+  }
+}
 
 struct SampleGeom {
   int it, ix, iy;     // keyframe cell per axis at this level
@@ -269,13 +302,13 @@ __global__ void __launch_bounds__(kGridThreads) grid_gather_kernel(const GridArg
   }
 
   // 3x3 neighbourhood of the nearest voxel (same t slice), all weights 1.
-  const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
+  const SparseTime stime = sparse_time(a, t);
+  const int vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
   for (int v = l; v < 9; v += L) {
     const int di = v / 3 - 1, dj = v - (v / 3) * 3 - 1;
     const int cx = min(max(vx + di, 0), a.xres - 1), cy = min(max(vy + dj, 0), a.yres - 1);
-    const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
     float fv[F3];
-    ld_feat<F3>(a.sparse + vox * F3, fv);
+    sparse_fetch<F3>(a, stime, cx, cy, fv);
     if (a.z != nullptr) {
 #pragma unroll
       for (int f = 0; f < F3; ++f) a.z[s * a.ldz + 3 * pw + v * F3 + f] = fv[f];
@@ -589,7 +622,8 @@ __global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArg
     return;
   }
   const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
-  const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
+  const SparseTime stime = sparse_time(a, t);
+  const int vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
   float vals[NCH * 8];
 #pragma unroll
   for (int i = 0; i < NCH * 8; ++i) vals[i] = (i == NV) ? 1.0f : 0.0f;
@@ -597,9 +631,8 @@ __global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArg
   for (int v = 0; v < 9; ++v) {
     const int di = v / 3 - 1, dj = v - (v / 3) * 3 - 1;
     const int cx = min(max(vx + di, 0), a.xres - 1), cy = min(max(vy + dj, 0), a.yres - 1);
-    const size_t vox = (static_cast<size_t>(vt) * a.xres + cx) * a.yres + cy;
     float fv[F3];
-    ld_feat<F3>(a.sparse + vox * F3, fv);
+    sparse_fetch<F3>(a, stime, cx, cy, fv);
 #pragma unroll
     for (int f = 0; f < F3; ++f) vals[v * F3 + f] = fv[f];
   }
@@ -690,7 +723,7 @@ int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
 }  // namespace
 
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, int64_t n,
-                       float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st) {
+                       float* z, int ldz, uint8_t* z16t, int kz, cudaStream_t st, bool temporal_interp) {
   GridArgs a{};
   a.tab = tab;
   a.coords = coords;
@@ -699,6 +732,7 @@ int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params*
   a.sparse = p->sparse;
   a.z = z; a.ldz = ldz; a.z16t = z16t; a.kz = kz; a.n_pad = (n + 127) / 128 * 128;
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
+  a.interp = temporal_interp ? 1 : 0;
   a.scale = 1.0f;
   if (z == nullptr && z16t != nullptr && (tab.n_levels * d->n_features) % 8 == 0 && n >= 4096) {
     switch (d->n_features) {

@@ -342,10 +342,10 @@ size_t carve(const nvp_desc* d, int64_t chunk, int what, void* base, Workspace* 
 }
 
 int forward_chunk(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, const float* tau,
-                  int64_t n, const Workspace& w, float* rgb_out, cudaStream_t st) {
+                  int64_t n, const Workspace& w, float* rgb_out, cudaStream_t st, bool temporal_interp = false) {
   const int Z = latent_dim(d);
   int rc;
-  if ((rc = launch_grid_gather(d, tab, p, coords, n, w.z, w.ldz, nullptr, 0, st))) return rc;
+  if ((rc = launch_grid_gather(d, tab, p, coords, n, w.z, w.ldz, nullptr, 0, st, temporal_interp))) return rc;
   // modulator layer 0
   if ((rc = linear_nt(w.z, w.ldz, Z, p->mod_w[0], Z, p->mod_b[0], 1, 0, w.h[0], n, st))) return rc;
   siren0_fwd_kernel<<<row_blocks(n), H, 0, st>>>(tau, p->siren_w[0], p->siren_b[0], d->w0_first, w.h[0], w.a[0], n);
@@ -372,13 +372,13 @@ size_t simt_workspace_bytes(const nvp_desc* d, int64_t n, int what) {
 }
 
 int simt_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, const float* tsteps,
-                 int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st, bool temporal_interp) {
   NVP_CHECK(ws_bytes >= simt_workspace_bytes(d, n, 0), "workspace too small (see nvp_workspace_bytes)");
   for (int64_t s0 = 0; s0 < n; s0 += kChunk) {
     const int64_t m = std::min(kChunk, n - s0);
     Workspace w;
     carve(d, std::min(n, kChunk), 0, ws, &w);
-    int rc = forward_chunk(d, tab, p, coords + 3 * s0, tsteps + s0, m, w, out_rgb + 3 * s0, st);
+    int rc = forward_chunk(d, tab, p, coords + 3 * s0, tsteps + s0, m, w, out_rgb + 3 * s0, st, temporal_interp);
     if (rc) return rc;
   }
   return 0;

@@ -1116,14 +1116,14 @@ int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w,
 size_t tc_workspace_bytes(const nvp_desc* d, int64_t n, int what) { return carve_tc(d, std::max<int64_t>(n, 1), what, nullptr).total; }
 
 int tc_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, const float* tsteps,
-               int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st) {
+               int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st, bool temporal_interp) {
   NVP_CHECK(ws_bytes >= tc_workspace_bytes(d, n, 0), "workspace too small (see nvp_workspace_bytes)");
   void* base = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
   const TcWorkspace w = carve_tc(d, n, 0, base);
   const Dims m = make_dims(d);
   int rc;
   if ((rc = pack_forward_weights(d, p, w.wpk_fwd, nullptr, st))) return rc;
-  if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st))) return rc;
+  if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st, temporal_interp))) return rc;
   return launch_forward(d, p, w, tsteps, n, out_rgb, false, st);
 }
 

@@ -87,3 +87,52 @@ class VideoTimeWrapper(torch.utils.data.Dataset):
         temporal_steps = self.temporal_steps[temporal_coord_idx]
         all_coords = torch.cat((temporal_coords.unsqueeze(1), spatial_coords), dim=1)
         return {'all_coords': all_coords, "temporal_steps": temporal_steps}, {'img': data}
+
+
+class DeviceSampler:
+    """VideoTimeWrapper with the video resident in HBM and the batch produced by one kernel.
+
+    sample(step)                      throughput mode: Philox stream keyed by (seed, step); no host work, no H2D.
+    sample_indices(t_idx, p_idx)      parity mode: the reference's CPU index stream (dataio.py:106-107) uploaded;
+                                      the batch is bit-identical to VideoTimeWrapper.__getitem__.
+    Both return ({'all_coords': [1,N,3], 'temporal_steps': [1,N]}, {'img': uint8 [1,N,3]}) on the device.
+    """
+
+    def __init__(self, video, n_samples=1245184, device="cuda", seed=0, t_range=None):
+        from . import _lib
+        self._lib = _lib
+        vid = torch.as_tensor(video)
+        assert vid.dtype == torch.uint8 and vid.dim() == 4 and vid.shape[-1] == 3
+        self.T, self.H, self.W = int(vid.shape[0]), int(vid.shape[1]), int(vid.shape[2])
+        self.video = vid.reshape(self.T, self.H * self.W, 3).to(device).contiguous()
+        half_dt = 0.5 / self.T
+        self.temporal_steps = torch.linspace(half_dt, 1 - half_dt, self.T).to(device)
+        self.temporal_coords = torch.linspace(0, 1, self.T).to(device)
+        self.N_samples, self.seed = n_samples, seed
+        self.t_range = t_range or (0, self.T)
+        self.device = self.video.device
+
+    def _run(self, n, t_idx, p_idx, step, want_indices=False):
+        dev = self.device
+        coords = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        tsteps = torch.empty(n, dtype=torch.float32, device=dev)
+        gt = torch.empty(n, 3, dtype=torch.uint8, device=dev)
+        ti = torch.empty(n, dtype=torch.int32, device=dev) if want_indices else None
+        pi = torch.empty(n, dtype=torch.int32, device=dev) if want_indices else None
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        with torch.cuda.device(dev):
+            rc = self._lib.load().nvp_sample_batch(
+                self.video.data_ptr(), self.T, self.H, self.W, self.temporal_coords.data_ptr(), self.temporal_steps.data_ptr(),
+                n, ptr(t_idx), ptr(p_idx), self.seed, step, self.t_range[0], self.t_range[1], coords.data_ptr(),
+                tsteps.data_ptr(), gt.data_ptr(), ptr(ti), ptr(pi), torch.cuda.current_stream(dev).cuda_stream)
+        self._lib.check(rc, "nvp_sample_batch")
+        out = ({"all_coords": coords[None], "temporal_steps": tsteps[None]}, {"img": gt[None]})
+        return out + ((ti, pi),) if want_indices else out
+
+    def sample(self, step: int, want_indices=False):
+        return self._run(self.N_samples, None, None, step, want_indices)
+
+    def sample_indices(self, t_idx: torch.Tensor, p_idx: torch.Tensor):
+        t_idx = t_idx.to(self.device, torch.int64).contiguous()
+        p_idx = p_idx.to(self.device, torch.int64).contiguous()
+        return self._run(t_idx.numel(), t_idx, p_idx, 0)

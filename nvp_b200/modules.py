@@ -78,7 +78,11 @@ class NVP(nn.Module):
         tsteps = timesteps.reshape(b * t)
         coords = model_input["all_coords"].reshape(-1, 3)  # t, x, y
         if temporal_interp:
-            raise NotImplementedError("temporal_interp=True (SparseGrid.forward_inter, eval-only) is not built yet")
+            # eval-only path (eval.py:239 with --t_interp): SparseGrid.forward_inter, forward kernel only
+            with torch.no_grad():
+                out = functional.forward(self.desc, self.hot_path_parameters(), coords, tsteps,
+                                         self.mode | _lib.FLAG_TEMPORAL_INTERP)
+            return {"model_out": out.reshape(b, t, 3)}
         out = functional.NvpFunction.apply(self.desc, self.mode, coords, tsteps, *self.hot_path_parameters())
         return {"model_out": out.reshape(b, t, 3)}
 

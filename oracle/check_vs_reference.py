@@ -118,6 +118,17 @@ def check(cfg: O.NVPConfig, n=512, seed=0, grid_std=0.5, verbose=True):
     sg = ref.sparsegrid.SparseGrid(cfg.sparse_features, cfg.x_resolution, cfg.y_resolution, cfg.t_resolution, False)
     sg.embeddings.data.copy_(p["sparse_grid.embeddings"])
     res["sparse_max_abs"] = float((sg(coords) - O.sparse_grid_forward(p["sparse_grid.embeddings"], coords)).abs().max())
+    # eval-time temporal interpolation (sparsegrid.py:76-156), fractional frame positions; NaN at t == 1 in both
+    ci = coords.clone()
+    ci[:, 0] = torch.rand(n, generator=g) * 0.999
+    ci[:4, 0] = torch.tensor([0.0, 1.0, 0.5, 1.0 / (cfg.t_resolution - 1)])
+    a, b = sg.forward_inter(ci).detach(), O.sparse_grid_forward_inter(p["sparse_grid.embeddings"], ci)
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    res["sparse_inter_max_abs"] = float((torch.nan_to_num(a) - torch.nan_to_num(b)).abs().max())
+    with torch.no_grad():
+        oi = model({"all_coords": ci[None], "temporal_steps": tsteps[None]}, temporal_interp=True)["model_out"][0]
+    mine = O.nvp_forward(p, ci, tsteps, cfg, temporal_interp=True)
+    res["fwd_inter_max_abs"] = float((torch.nan_to_num(oi) - torch.nan_to_num(mine)).abs().max())
     if verbose:
         for k, v in res.items():
             print(f"  {k:55s} {v:.3e}")

@@ -15,6 +15,7 @@ What each function restates (citations relative to /root/reference):
                          include/tiny-cuda-nn/encodings/grid.h semantics (pos = fma(scale,x,0.5),
                          floor/fract, 4-corner bilinear, flat index modulo level size, dim-0 fastest).
   sparse_grid_forward    sparsegrid.py:23-72   (nearest voxel + 3x3 (x,y) neighbourhood, clamped)
+  sparse_grid_forward_inter  sparsegrid.py:76-156 (eval-only temporal blend of two t-slices)
   modulator_forward      modulation.py:96-121  (LeakyReLU(0.01) MLP with skip-concat of the latent)
   siren_forward          modulation.py:20-56,60-92 (sin(w0*(Wx+b)), in-place gating by the modulator)
   nvp_forward            modules.py:51-84      (concat order xy, yt, xt, sparse; plane inputs
@@ -160,6 +161,34 @@ def sparse_grid_forward(emb: torch.Tensor, coords: torch.Tensor) -> torch.Tensor
     return torch.cat(feats, dim=1)
 
 
+def sparse_grid_forward_inter(emb: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
+    """Eval-time temporal interpolation (sparsegrid.py:76-156): blend of the t-slices below / above the sample.
+
+    Restated with the reference's quirk (sparsegrid.py:108-109): upper is normalised first and the lower coefficient
+    is then divided by (NEW upper + lower); at the last frame both raw coefficients are 0 and the result is NaN,
+    exactly as in the reference."""
+    T, X, Y, F = emb.shape
+    c = np.ascontiguousarray(coords.detach().cpu().numpy(), np.float32)
+    tf = (np.float32(T - 1) * c[:, 0]).astype(np.float32)
+    lower = tf.astype(np.int64)
+    upper = np.clip((tf + np.float32(1)).astype(np.float32).astype(np.int64), 0, T - 1)
+    up = (tf - lower.astype(np.float32)).astype(np.float32)
+    lo = (upper.astype(np.float32) - tf).astype(np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        up = (up / (up + lo)).astype(np.float32)
+        lo = (lo / (up + lo)).astype(np.float32)
+    _, xi, yi = sparse_grid_indices(c, T, X, Y)
+    lo_t, up_t = torch.from_numpy(lo).to(emb.dtype)[:, None], torch.from_numpy(up).to(emb.dtype)[:, None]
+    lower_t, upper_t = torch.from_numpy(lower), torch.from_numpy(upper)
+    feats = []
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            vx = torch.from_numpy(np.clip(xi + i, 0, X - 1))
+            vy = torch.from_numpy(np.clip(yi + j, 0, Y - 1))
+            feats.append(emb[lower_t, vx, vy, :] * lo_t + emb[upper_t, vx, vy, :] * up_t)
+    return torch.cat(feats, dim=1)
+
+
 # --------------------------------------------------------------------------------------------
 # Modulated SIREN (modulation.py)
 # --------------------------------------------------------------------------------------------
@@ -242,21 +271,21 @@ class NVPConfig:
         return 3 * self.n_levels * self.n_features + 9 * self.sparse_features
 
 
-def latent_forward(p: Dict[str, torch.Tensor], coords: torch.Tensor, cfg: NVPConfig) -> torch.Tensor:
-    """z = [DG_xy(x,y) | DG_yt(t,y) | DG_xt(t,x) | SG(t,x,y)]   (modules.py:61-78)."""
+def latent_forward(p: Dict[str, torch.Tensor], coords: torch.Tensor, cfg: NVPConfig, temporal_interp: bool = False) -> torch.Tensor:
+    """z = [DG_xy(x,y) | DG_yt(t,y) | DG_xt(t,x) | SG(t,x,y)]   (modules.py:61-78; temporal_interp: modules.py:72-73)."""
     tab = cfg.table
     c = coords.reshape(-1, 3)
     xy = dense_grid_forward(p["keyframes_xy.params"], c[:, [1, 2]], cfg.n_features, tab)
     xt = dense_grid_forward(p["keyframes_xt.params"], c[:, [0, 1]], cfg.n_features, tab)
     yt = dense_grid_forward(p["keyframes_yt.params"], c[:, [0, 2]], cfg.n_features, tab)
-    sg = sparse_grid_forward(p["sparse_grid.embeddings"], c)
+    sg = (sparse_grid_forward_inter if temporal_interp else sparse_grid_forward)(p["sparse_grid.embeddings"], c)
     return torch.cat((xy, yt, xt, sg), dim=1)
 
 
 def nvp_forward(p: Dict[str, torch.Tensor], coords: torch.Tensor, tsteps: torch.Tensor, cfg: NVPConfig,
-                mma_dtype=None) -> torch.Tensor:
+                mma_dtype=None, temporal_interp: bool = False) -> torch.Tensor:
     """coords [N,3]=(t,x,y), tsteps [N] -> rgb [N,3]."""
-    z = latent_forward(p, coords, cfg)
+    z = latent_forward(p, coords, cfg, temporal_interp)
     mods = modulator_forward(z, p, cfg.n_hidden_layers, mma_dtype)
     return siren_forward(tsteps.reshape(-1, 1).to(z.dtype), mods, p, cfg.n_hidden_layers, mma_dtype=mma_dtype)
 

@@ -226,3 +226,21 @@ def test_full_size_config_s_properties(mode):
     # and all three planes see every sample once per level
     sg = m.sparse_grid.embeddings.grad
     assert float(sg.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n", [300, 5000])
+def test_temporal_interp_forward_matches_oracle(n, mode):
+    """eval-time NVP.forward(temporal_interp=True) = SparseGrid.forward_inter (sparsegrid.py:76-156), incl. NaN at t=1."""
+    cfg = O.NVPConfig(t_resolution=9, x_resolution=21, y_resolution=17)
+    p = O.init_params(cfg, seed=31, grid_std=0.4)
+    g = torch.Generator().manual_seed(n)
+    coords = torch.rand(n, 3, generator=g)
+    coords[:4, 0] = torch.tensor([0.0, 1.0, 0.5, 1.0 / 8])
+    tsteps = torch.rand(n, generator=g)
+    ref = O.nvp_forward({k: v.double() for k, v in p.items()}, coords.double(), tsteps.double(), cfg, temporal_interp=True)
+    m = make_model(cfg, p, mode=mode)
+    out = m({"all_coords": dev(coords)[None], "temporal_steps": dev(tsteps)[None]}, temporal_interp=True)["model_out"][0].cpu()
+    assert torch.equal(torch.isnan(out).any(dim=1), torch.isnan(ref).any(dim=1))
+    ok = ~torch.isnan(ref).any(dim=1)
+    assert float((out[ok].double() - ref[ok]).abs().max()) <= FWD_TOL[mode]

@@ -59,12 +59,12 @@ def test_same_seed_gives_reference_initial_weights():
             assert torch.equal(sa[k], sb[k]), k
 
 
-def test_cpu_tensors_fail_loudly_and_interp_is_gated():
+def test_cpu_tensors_fail_loudly():
     m = nvp_b200.NVP(out_features=3, encoding_config=small_json())
     x = {"all_coords": torch.rand(1, 8, 3), "temporal_steps": torch.rand(1, 8)}
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(x)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         m(x, temporal_interp=True)
     with pytest.raises(ValueError):
         nvp_b200.NVP(out_features=3, encoding_config=small_json(), mode="triton")
