@@ -130,6 +130,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def measured_traffic(config: str):
+    """DRAM bytes per step and kernel kind from the committed `ncu --set full` capture of prof_step.py (same workload)."""
+    path = os.path.join(ROOT, "profiles", f"r01_traffic_{config}.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)["dram_bytes_per_step"]
+    return {}
+
+
 # Algorithmic work per pixel (SURVEY.md 8(d); every gathered/scattered element counted once, no cache credit).
 def algorithmic_work(F: int):
     G = (3 * 16 * 4 + 9) * F * 4          # grid gather bytes / px  (1608 B for S)
@@ -329,25 +338,29 @@ def run_ours(args):
         peaks = measured_peaks()
         work = algorithmic_work(F)
         kernels = {}
+        traffic = measured_traffic(args.config)
         for name, (ms, cnt) in kern.items():
             if cnt == 0:
                 continue
-            avg = ms / cnt
-            ent = {"launches": cnt, "avg_ms": avg, "share_of_step": ms / ms_total}
+            per_step = ms / args.steps            # all launches of this kind in one step (gather / scatter launch two kernels)
+            ent = {"launches_per_step": cnt / args.steps, "ms_per_step": per_step, "share_of_step": ms / ms_total}
             if name in work:
                 bound, per_px = work[name]
-                per_launch = per_px * n
+                per_step_work = per_px * n
                 if bound == "hbm":
-                    ent.update(bound="hbm", achieved=per_launch / (avg * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+                    ent.update(bound="hbm", achieved=per_step_work / (per_step * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
                 else:
-                    ent.update(bound="tensor", achieved=per_launch / (avg * 1e-3) / 1e12, peak=peaks["tflops_sustained"], unit="TFLOP/s")
+                    ent.update(bound="tensor", achieved=per_step_work / (per_step * 1e-3) / 1e12, peak=peaks["tflops_sustained"], unit="TFLOP/s")
                 ent["frac"] = ent["achieved"] / ent["peak"]
-                ent["algorithmic_per_launch"] = per_launch
+                ent["algorithmic_per_step"] = per_step_work
+                ent["traffic"] = traffic.get(name)
             kernels[name] = ent
-        dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
+        dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
         d = kernels[dom]
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": d["frac"], "traffic": d["traffic"], "peak_source": peaks["source"],
+                    "note": "achieved = algorithmic bytes (SURVEY 8(d): every gathered/scattered element once) / CUDA-event time of the "
+                            "kind per step; traffic = ncu dram bytes per step from profiles/ (null if no capture for this config)",
                     "whole_step": {"hbm_frac": work["total_bytes"] * n / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                    "tensor_frac": work["total_flop"] * n / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]}}
         out = {

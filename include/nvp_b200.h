@@ -112,6 +112,12 @@ int nvp_workspace_bytes(const nvp_desc* d, int64_t n, int mode, int what, size_t
 int nvp_encode_latent(const nvp_desc* d, const nvp_params* p, const float* coords, int64_t n,
                       float* z, void* stream);
 
+/* Backward of nvp_encode_latent: grid gradients += scatter of dz[N, Z] (fp32).  Only the four grid pointers of `g` are
+ * used (NULL = skip).  With nvp_encode_latent this is the autograd pair behind the standalone operators the reference
+ * calls: tcnn.Encoding.__call__ (modules.py:65-67) and SparseGrid.forward (sparsegrid.py:23-72). */
+int nvp_scatter_latent(const nvp_desc* d, const float* coords, int64_t n, const float* dz, const nvp_grads* g,
+                       void* stream);
+
 /* out_rgb[N,3] = NVP.forward. */
 int nvp_forward(const nvp_desc* d, const nvp_params* p, const float* coords, const float* tsteps,
                 int64_t n, float* out_rgb, void* workspace, size_t workspace_bytes, int mode,

@@ -42,7 +42,7 @@ class NvpPtrs(C.Structure):
 EXPORTS = (
     "nvp_version", "nvp_last_error", "nvp_level_table", "nvp_latent_dim", "nvp_workspace_bytes",
     "nvp_encode_latent", "nvp_forward", "nvp_backward", "nvp_fwd_loss_bwd", "nvp_last_launch_count",
-    "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step", "nvp_sample_batch",
+    "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step", "nvp_sample_batch", "nvp_scatter_latent",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
     lib.nvp_level_table.argtypes = [D, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     lib.nvp_workspace_bytes.argtypes = [D, i64, i32, i32, C.POINTER(C.c_size_t)]
     lib.nvp_encode_latent.argtypes = [D, P, vp, i64, vp, vp]
+    lib.nvp_scatter_latent.argtypes = [D, vp, i64, vp, P, vp]
     lib.nvp_forward.argtypes = [D, P, vp, vp, i64, vp, vp, C.c_size_t, i32, vp]
     lib.nvp_backward.argtypes = [D, P, vp, vp, vp, i64, P, vp, C.c_size_t, i32, vp]
     lib.nvp_fwd_loss_bwd.argtypes = [D, P, vp, vp, vp, i64, i64, P, vp, vp, vp, C.c_size_t, i32, vp]

@@ -175,6 +175,19 @@ int nvp_encode_latent(const nvp_desc* d, const nvp_params* p, const float* coord
   return launch_grid_gather(d, tab, p, coords, n, z, latent_dim(d), nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
+int nvp_scatter_latent(const nvp_desc* d, const float* coords, int64_t n, const float* dz, const nvp_grads* g, void* stream) {
+  reset_launch_count();
+  LevelTab tab;
+  if (int rc = build_level_table(d, &tab, nullptr)) return rc;
+  NVP_CHECK(n >= 0, "n must be >= 0");
+  NVP_CHECK(g != nullptr, "nvp_grads is NULL");
+  if (n == 0) return 0;
+  if (int rc = check_device_ptr(coords, "coords")) return rc;
+  if (int rc = check_device_ptr(dz, "dz")) return rc;
+  return launch_grid_scatter(d, tab, coords, n, dz, latent_dim(d), nullptr, 0, 1.0f, nullptr, g,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int nvp_forward(const nvp_desc* d, const nvp_params* p, const float* coords, const float* tsteps, int64_t n,
                 float* out_rgb, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   reset_launch_count();

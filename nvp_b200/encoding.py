@@ -29,11 +29,26 @@ class Encoding(nn.Module):
         desc = _lib.NvpDesc(self.n_features, self.n_levels, encoding_config["base_resolution"],
                             encoding_config["per_level_scale"], 1, 1, 1, 1, 128, 3, 30.0)
         self.level_scales, self.level_res, self.level_offsets = _lib.level_table(desc)
+        self._op_desc = desc   # xy plane + 1x1x1 dummy 3-D grid with one feature: latent = [this plane | 2 dummies | 9]
         n_params = self.level_offsets[-1] * self.n_features
         # tcnn initialises U(-1e-4, 1e-4) from its own pcg32 (seed 1337, identical for the three planes) and
         # does not touch torch's global RNG; a private generator keeps both properties.
         g = torch.Generator().manual_seed(seed)
         self.params = nn.Parameter((torch.rand(n_params, generator=g) * 2 - 1) * 1e-4)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """[N,2] in [0,1] -> [N, n_levels*F] (level-major), differentiable w.r.t. `.params` — the standalone
+        tcnn.Encoding.__call__ of modules.py:65-67.  Runs the same gather / scatter kernels as the fused model:
+        the inputs are presented as the xy plane of a latent whose other planes and 3-D grid are dummies."""
+        from . import functional
+        if not x.is_cuda:
+            raise RuntimeError("Encoding input is a CPU tensor: nvp_b200 has no CPU path")
+        n = x.shape[0]
+        coords = torch.cat((torch.zeros(n, 1, device=x.device, dtype=torch.float32), x.to(torch.float32)), dim=1)
+        dummy_plane = self.params.detach()
+        dummy_grid = torch.zeros(1, 1, 1, 1, device=x.device, dtype=torch.float32)
+        z = functional.LatentFunction.apply(self._op_desc, coords, self.params, dummy_plane, dummy_plane, dummy_grid)
+        return z[:, : self.n_output_dims]
 
     def extra_repr(self):
         return f"DenseGrid levels={self.n_levels} F={self.n_features} params={self.params.numel()}"

@@ -162,3 +162,33 @@ class NvpFunction(torch.autograd.Function):
         grads = [torch.zeros_like(p) if ctx.needs_input_grad[4 + i] else None for i, p in enumerate(params)]
         backward(ctx.desc, params, grads, coords, tsteps, dout.reshape(-1, 3), ctx.mode)
         return (None, None, None, None, *grads)
+
+
+def scatter_latent(desc: _lib.NvpDesc, grads: Sequence[Optional[torch.Tensor]], coords: torch.Tensor, dz: torch.Tensor) -> None:
+    """grads[0..3] (kf_xy, kf_yt, kf_xt, sparse; None = skip) += backward of encode_latent for upstream dz [N, Z]."""
+    coords = _require_cuda("all_coords", coords, torch.float32)
+    dz = _require_cuda("grad of the latent", dz, torch.float32)
+    gs: List[Optional[torch.Tensor]] = list(grads[:4]) + [None] * (len(PARAM_ORDER) - 4)
+    with torch.cuda.device(coords.device):
+        gg = pack_ptrs(gs)
+        rc = _lib.load().nvp_scatter_latent(C.byref(desc), coords.data_ptr(), coords.shape[0], dz.data_ptr(), C.byref(gg),
+                                            _stream_ptr(coords.device))
+    _lib.check(rc, "nvp_scatter_latent")
+    _note_launches()
+
+
+class LatentFunction(torch.autograd.Function):
+    """z = [DG_xy | DG_yt | DG_xt | SG](coords) with gradients for the four grid tensors (none for coords)."""
+
+    @staticmethod
+    def forward(ctx, desc, coords, kf_xy, kf_yt, kf_xt, sparse):
+        ctx.desc = desc
+        ctx.save_for_backward(coords, kf_xy, kf_yt, kf_xt, sparse)
+        return encode_latent(desc, [kf_xy, kf_yt, kf_xt, sparse], coords)
+
+    @staticmethod
+    def backward(ctx, dz):
+        coords, *grids = ctx.saved_tensors
+        grads = [torch.zeros_like(p) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(grids)]
+        scatter_latent(ctx.desc, grads, coords, dz.contiguous())
+        return (None, None, *grads)

@@ -244,3 +244,39 @@ def test_temporal_interp_forward_matches_oracle(n, mode):
     assert torch.equal(torch.isnan(out).any(dim=1), torch.isnan(ref).any(dim=1))
     ok = ~torch.isnan(ref).any(dim=1)
     assert float((out[ok].double() - ref[ok]).abs().max()) <= FWD_TOL[mode]
+
+
+@pytest.mark.parametrize("F", [2, 4])
+def test_standalone_encoding_and_sparse_grid_operators(F):
+    """Inner operator boundary: tcnn.Encoding.__call__ and SparseGrid.forward as autograd ops."""
+    from nvp_b200.encoding import Encoding
+    from nvp_b200.sparsegrid import SparseGrid
+    cfg = O.NVPConfig(n_features=F, sparse_features=F, t_resolution=5, x_resolution=12, y_resolution=9)
+    p = O.init_params(cfg, seed=40 + F, grid_std=0.3)
+    n = 5000
+    g = torch.Generator().manual_seed(F)
+    u = torch.rand(n, 2, generator=g)
+    u[:3] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [1.0, 0.25]])
+    enc = Encoding(2, cfg.to_json()["2d_encoding_xy"]).cuda()
+    enc.params.data.copy_(p["keyframes_xy.params"])
+    out = enc(u.cuda())
+    pr = p["keyframes_xy.params"].clone().double().requires_grad_(True)
+    ref = O.dense_grid_forward(pr, u, F, cfg.table)
+    assert out.shape == (n, 16 * F) and float((out.cpu() - ref.detach()).abs().max()) <= 1e-6
+    w = torch.randn(n, 16 * F, generator=g)
+    (out * w.cuda()).sum().backward()
+    (ref * w.double()).sum().backward()
+    assert rel_err(enc.params.grad.cpu(), pr.grad) <= 2e-5
+
+    c3 = torch.rand(n, 3, generator=g)
+    c3[:2] = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]])
+    sg = SparseGrid(F, cfg.x_resolution, cfg.y_resolution, cfg.t_resolution).cuda()
+    sg.embeddings.data.copy_(p["sparse_grid.embeddings"])
+    so = sg(c3.cuda())
+    er = p["sparse_grid.embeddings"].clone().double().requires_grad_(True)
+    sr = O.sparse_grid_forward(er, c3)
+    assert so.shape == (n, 9 * F) and float((so.cpu() - sr.detach()).abs().max()) <= 1e-7
+    w2 = torch.randn(n, 9 * F, generator=g)
+    (so * w2.cuda()).sum().backward()
+    (sr * w2.double()).sum().backward()
+    assert rel_err(sg.embeddings.grad.cpu(), er.grad) <= 2e-5

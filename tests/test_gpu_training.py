@@ -77,3 +77,29 @@ def test_loss_curve_and_psnr_match_the_oracle_at_equal_steps(tmp_path):
         np.testing.assert_allclose(got[0], ref[0], rtol=1e-5 if mode == "fp32" else 1e-3)
         np.testing.assert_allclose(got, ref, rtol=rtol, err_msg=mode)
         assert abs(10 * math.log10(4 / got[-1]) - psnr_ref) <= dpsnr, mode
+
+
+def test_eval_helpers_render_quantise_and_psnr():
+    """eval.py path: quantise the grids to 8 bit (per level / feature min-max), render a frame in slices, PSNR."""
+    from nvp_b200 import eval_utils
+    T, Hh, Ww = 8, 40, 50
+    cfg = O.NVPConfig(t_resolution=T, x_resolution=16, y_resolution=16)
+    p = O.init_params(cfg, seed=2, grid_std=0.3)
+    m = make_model(cfg, p, mode="tc")
+    img = eval_utils.render_frame(m, 3, T, (Hh, Ww), n_slices=10)
+    assert img.shape == (3, Hh, Ww) and float(img.min()) >= 0 and float(img.max()) <= 1
+    # oracle for the same frame
+    coords = torch.cat((torch.linspace(0, 1, T)[3] * torch.ones(Hh * Ww, 1), dataio.get_mgrid((Hh, Ww), 2)), dim=1)
+    tsteps = torch.linspace(0.5 / T, 1 - 0.5 / T, T)[3] * torch.ones(Hh * Ww)
+    ref = torch.clamp((O.nvp_forward(p, coords, tsteps, cfg).view(Hh, Ww, 3).permute(2, 0, 1) + 1) / 2, 0, 1)
+    assert float((img.cpu() - ref).abs().max()) <= 1e-3
+    assert eval_utils.psnr(img.cpu(), ref) > 60
+    before = m.keyframes_xy.params.detach().clone()
+    eval_utils.quantize_model(m)
+    err = (m.keyframes_xy.params.detach() - before).abs().max()
+    assert 0 < float(err) <= 0.3 * 2 / 255 + 1e-6        # at most one 8-bit step of the widest level range
+    q = eval_utils.render_frame(m, 3, T, (Hh, Ww), n_slices=10)
+    assert eval_utils.psnr(q.cpu(), ref) > 30
+    # temporal interpolation rendering (eval.py --t_interp): frames between key frames are finite away from t=1
+    mid = eval_utils.render_frame(m, 5, 2 * T, (Hh, Ww), org_nframes=T, temporal_interp=True, n_slices=10)
+    assert torch.isfinite(mid).all()
