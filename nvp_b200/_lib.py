@@ -120,7 +120,7 @@ def workspace_bytes(desc: NvpDesc, n: int, mode: int, what: int) -> int:
     return int(out.value)
 
 
-PROFILE_KINDS = ("pack", "grid_gather", "mlp_forward", "mlp_backward", "mlp_wgrad", "grid_scatter", "fp32_mode", "misc")
+PROFILE_KINDS = ("pack", "grid_gather", "mlp_forward", "mlp_backward", "mlp_wgrad", "grid_scatter", "fp32_mode", "misc", "grid_bin")
 
 
 def profile_enable(on: bool) -> None:

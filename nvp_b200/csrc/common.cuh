@@ -45,7 +45,7 @@ void reset_launch_count();
   } while (0)
 
 // Optional per-kernel CUDA-event timing (nvp_profile_enable / nvp_profile_read in the C ABI).
-enum KernelId { K_PACK = 0, K_GATHER, K_MLP_FWD, K_MLP_BWD, K_MLP_WGRAD, K_SCATTER, K_SIMT, K_MISC, K_COUNT };
+enum KernelId { K_PACK = 0, K_GATHER, K_MLP_FWD, K_MLP_BWD, K_MLP_WGRAD, K_SCATTER, K_SIMT, K_MISC, K_BIN, K_COUNT };
 void prof_start(int id, cudaStream_t st);
 void prof_stop(cudaStream_t st);
 struct ScopedKernelTimer {
@@ -79,6 +79,19 @@ int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params*
 int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
                         const float* dz, int lddz, const uint8_t* dz16t, int kz, float scale, const float* scale_ptr,
                         const nvp_grads* g, cudaStream_t st);
+
+// Tile-binned variant for the tensor-core path (grid_binned.cuh): samples are bucketed per keyframe plane by the tile
+// of the unit square they fall into (launch_grid_bin, once per call) and the gather / scatter-add work on private
+// shared-memory windows.  grid_bin_workspace_bytes == 0 means "not available for this configuration".
+size_t grid_bin_workspace_bytes(const nvp_desc* d, const LevelTab& tab, int64_t n);
+int launch_grid_bin(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, int kz, void* binws,
+                    cudaStream_t st);
+int launch_grid_gather_binned(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+                              int64_t n, uint8_t* z16t, int kz, void* binws, cudaStream_t st,
+                              bool temporal_interp = false);
+int launch_grid_scatter_binned(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
+                               const uint8_t* dz16t, int kz, float scale, const float* scale_ptr, const nvp_grads* g,
+                               void* binws, cudaStream_t st);
 
 // ---- mlp_simt.cu --------------------------------------------------------------------------
 size_t simt_workspace_bytes(const nvp_desc* d, int64_t n, int what);

@@ -10,6 +10,9 @@
 // loads are warp-broadcasts.  Threads with level index < 9 also fetch one voxel of the 3x3
 // neighbourhood.  All table reads go through the read-only path as F-wide vectors; the backward
 // uses F-wide vector reductions (red.global.add.v2/v4.f32, sm_90+).
+#include <math.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -99,6 +102,7 @@ struct GridArgs {
   int n_coarse_chunks;     // gather v2: 16-byte chunks per plane handled by the coarse kernel
   int coarse_cells;        // offset[n_coarse]
   int64_t chunk;           // coarse kernel: samples per CTA
+  int zero_planes;         // gather_fine last pass: padding rows also clear the keyframe columns (binned path)
 };
 
 // Frame selection of the 3-D grid: nearest frame (sparsegrid.py:43-46) or, for temporal_interp, the blend of the
@@ -619,6 +623,8 @@ __global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArg
   const int total_chunks = (a.kz * 64 - c0) >> 3;
   if (s >= a.n) {
     for (int j = 0; j < total_chunks; ++j) *chunk_ptr(c0 + 8 * j) = make_uint4(0u, 0u, 0u, 0u);
+    if (a.zero_planes)
+      for (int c = 0; c < c0; c += 8) *chunk_ptr(c) = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
   const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
@@ -720,6 +726,116 @@ int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
   return 0;
 }
 
+#include "grid_binned.cuh"
+
+// ---- host side of the binned path -----------------------------------------------------------
+struct BinPlan {
+  BinTab bt;
+  int warps;            // warps (= private regions) per CTA
+  size_t smem;          // dynamic shared memory per CTA
+  int max_tasks;
+  size_t o_cnt, o_offs, o_cursor, o_ntasks, o_zeros, o_tasks, o_recs, total;   // workspace byte offsets
+};
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// false: this configuration does not use the binned path (the direct kernels serve it).
+bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl) {
+  const int L = tab.n_levels, F2 = d->n_features;
+  if (env_int("NVP_GRID_BINNED", 1) == 0) return false;
+  // 32-bit row offsets into the latent tile buffer (<= 4 panels per 128-sample tile) and 32-bit bucket positions
+  if ((L * F2) % 8 != 0 || n < 1 || n > 8000000) return false;
+  constexpr size_t kRegionBudget = 216 * 1024;
+  const int forced_tb = env_int("NVP_BIN_TB", 0);
+  BinTab bt{};
+  int warps = 0;
+  for (int tb = 32; tb <= 128; tb <<= 1) {   // 3 * tb^2 counters must fit the scan kernel's shared memory
+    if (forced_tb && tb != forced_tb) continue;
+    int base = 0;
+    for (int l = 0; l < L; ++l) {
+      int E = static_cast<int>(ceilf(tab.scale[l] / static_cast<float>(tb))) + 2;
+      E = std::max(3, std::min(E, tab.res[l] + 1));
+      bt.E[l] = E;
+      bt.base[l] = base;
+      bt.magic[l] = (1u << 20) / static_cast<uint32_t>(E) + 1u;
+      for (int idx = 0; idx < E * E; ++idx)   // the reciprocal trick must be exact on the whole window
+        if (static_cast<int>((static_cast<uint32_t>(idx) * bt.magic[l]) >> 20) != idx / E) return false;
+      base += E * E;
+    }
+    bt.base[L] = base;
+    bt.tb = tb; bt.nt = tb * tb;
+    bt.log_tb = 0;
+    while ((1 << bt.log_tb) < tb) ++bt.log_tb;
+    const size_t region = (static_cast<size_t>((base * F2 + 3) & ~3) + kStageFloats) * sizeof(float);   // + batch stage
+    warps = static_cast<int>(std::min<size_t>(kBinThreadsMax / 32, kRegionBudget / region));
+    if (warps >= kBinThreadsMax / 32 || forced_tb) break;
+    warps = 0;
+  }
+  if (warps < 1) return false;
+  warps = std::max(1, std::min(warps, env_int("NVP_BIN_WARPS", warps)));
+  const int64_t avg = (n + bt.nt - 1) / bt.nt;
+  int chunk = env_int("NVP_BIN_CHUNK", 0);
+  if (chunk <= 0) chunk = static_cast<int>(std::min<int64_t>(1 << 20, std::max<int64_t>(128, 2 * avg)));
+  bt.chunk = (chunk + 31) / 32 * 32;
+  pl->bt = bt;
+  pl->warps = warps;
+  pl->smem = static_cast<size_t>(warps) * (static_cast<size_t>((bt.base[L] * F2 + 3) & ~3) + kStageFloats) * sizeof(float);
+  pl->max_tasks = static_cast<int>(3 * static_cast<int64_t>(bt.nt) + 3 * n / bt.chunk + 8);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  pl->o_cnt = take(sizeof(int32_t) * 3 * bt.nt);
+  pl->o_offs = take(sizeof(int32_t) * (3 * bt.nt + 1));
+  pl->o_cursor = take(sizeof(int32_t) * 3 * bt.nt);
+  pl->o_ntasks = take(sizeof(int32_t));
+  pl->o_zeros = take(16);
+  pl->o_tasks = take(sizeof(int2) * pl->max_tasks);
+  pl->o_recs = take(sizeof(uint4) * 3 * static_cast<size_t>(n));
+  pl->total = off;
+  return true;
+}
+
+void fill_bin_args(const BinPlan& pl, const LevelTab& tab, const float* coords, int64_t n, void* ws, BinArgs* a) {
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  a->tab = tab; a->bt = pl.bt; a->coords = coords; a->n = static_cast<int32_t>(n);
+  a->cnt = reinterpret_cast<int32_t*>(b + pl.o_cnt);
+  a->offs = reinterpret_cast<int32_t*>(b + pl.o_offs);
+  a->cursor = reinterpret_cast<int32_t*>(b + pl.o_cursor);
+  a->n_tasks = reinterpret_cast<int32_t*>(b + pl.o_ntasks);
+  a->tasks = reinterpret_cast<int2*>(b + pl.o_tasks);
+  a->recs = reinterpret_cast<uint4*>(b + pl.o_recs);
+  a->zeros = reinterpret_cast<const uint4*>(b + pl.o_zeros);
+}
+
+int device_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+template <int F2, bool SCATTER>
+int launch_binned_kernel(const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
+  NVP_CUDA(cudaFuncSetAttribute(grid_binned_kernel<F2, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(pl.smem)));
+  const int blocks = std::max(1, std::min(device_sms(), (pl.max_tasks + pl.warps - 1) / pl.warps));
+  grid_binned_kernel<F2, SCATTER><<<blocks, pl.warps * 32, pl.smem, st>>>(a);
+  return 0;
+}
+template <bool SCATTER>
+int launch_binned(int f2, const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
+  switch (f2) {
+    case 1: return launch_binned_kernel<1, SCATTER>(pl, a, st);
+    case 2: return launch_binned_kernel<2, SCATTER>(pl, a, st);
+    case 4: return launch_binned_kernel<4, SCATTER>(pl, a, st);
+    case 8: return launch_binned_kernel<8, SCATTER>(pl, a, st);
+  }
+  set_error("n_features_per_level must be 1, 2, 4 or 8");
+  return 1;
+}
+
 }  // namespace
 
 int launch_grid_gather(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords, int64_t n,
@@ -790,5 +906,99 @@ int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coo
   }
   return dispatch(true, d->n_features, d->sparse_features, a, st);
 }
+
+// ---- binned path (see grid_binned.cuh) ---------------------------------------------------------
+size_t grid_bin_workspace_bytes(const nvp_desc* d, const LevelTab& tab, int64_t n) {
+  BinPlan pl;
+  return plan_bins(d, tab, n, &pl) ? pl.total + 256 : 0;
+}
+
+int launch_grid_bin(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, int kz, void* binws,
+                    cudaStream_t st) {
+  BinPlan pl;
+  NVP_CHECK(binws != nullptr && plan_bins(d, tab, n, &pl), "binned grid path not available for this configuration");
+  BinArgs a{};
+  fill_bin_args(pl, tab, coords, n, binws, &a);
+  a.kz = kz;
+  // counters, and (contiguous in the workspace) offs / cursor / n_tasks / the 16 zero bytes
+  NVP_CUDA(cudaMemsetAsync(a.cnt, 0, pl.o_tasks, st));
+  const int blocks = static_cast<int>(std::min<int64_t>(8 * device_sms(), (n + 255) / 256));
+  ScopedKernelTimer timer(K_BIN, st);
+  grid_bin_count_kernel<<<blocks, 256, 0, st>>>(a);
+  NVP_LAUNCH_CHECK();
+  const size_t scan_smem = sizeof(int32_t) * 3 * pl.bt.nt;
+  NVP_CUDA(cudaFuncSetAttribute(grid_bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem)));
+  grid_bin_scan_kernel<<<1, 1024, scan_smem, st>>>(a);
+  NVP_LAUNCH_CHECK();
+  grid_bin_fill_kernel<<<blocks, 256, 0, st>>>(a);
+  NVP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_grid_gather_binned(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
+                              int64_t n, uint8_t* z16t, int kz, void* binws, cudaStream_t st, bool temporal_interp) {
+  BinPlan pl;
+  NVP_CHECK(binws != nullptr && plan_bins(d, tab, n, &pl), "binned grid path not available for this configuration");
+  BinArgs b{};
+  fill_bin_args(pl, tab, coords, n, binws, &b);
+  b.kf[0] = p->kf_xy; b.kf[1] = p->kf_yt; b.kf[2] = p->kf_xt;
+  b.z16t = z16t; b.kz = kz;
+  {
+    ScopedKernelTimer timer(K_GATHER, st);
+    if (int rc = launch_binned<false>(d->n_features, pl, b, st)) return rc;
+    NVP_LAUNCH_CHECK();
+  }
+  // 3x3 voxel neighbourhood + padding columns (+ all-zero padding rows): the last pass of gather_fine_kernel
+  GridArgs a{};
+  a.tab = tab; a.coords = coords; a.n = n;
+  a.sparse = p->sparse;
+  a.z16t = z16t; a.kz = kz; a.n_pad = (n + 127) / 128 * 128;
+  a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
+  a.interp = temporal_interp ? 1 : 0;
+  a.scale = 1.0f;
+  a.n_coarse_chunks = tab.n_levels * d->n_features / 8;   // no keyframe passes
+  a.zero_planes = 1;
+  dim3 grid(static_cast<unsigned>((a.n_pad + kGridThreads - 1) / kGridThreads), 1);
+  ScopedKernelTimer timer(K_GATHER, st);
+  switch (d->n_features * 16 + d->sparse_features) {
+#define NVP_CASE(F2, F3) case F2 * 16 + F3: gather_fine_kernel<F2, F3><<<grid, kGridThreads, 0, st>>>(a); break;
+    NVP_CASE(1, 1) NVP_CASE(1, 2) NVP_CASE(1, 4) NVP_CASE(1, 8) NVP_CASE(2, 1) NVP_CASE(2, 2) NVP_CASE(2, 4) NVP_CASE(2, 8)
+    NVP_CASE(4, 1) NVP_CASE(4, 2) NVP_CASE(4, 4) NVP_CASE(4, 8) NVP_CASE(8, 1) NVP_CASE(8, 2) NVP_CASE(8, 4) NVP_CASE(8, 8)
+#undef NVP_CASE
+    default: NVP_CHECK(false, "n_features_per_level must be 1, 2, 4 or 8");
+  }
+  NVP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_grid_scatter_binned(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n,
+                               const uint8_t* dz16t, int kz, float scale, const float* scale_ptr, const nvp_grads* g,
+                               void* binws, cudaStream_t st) {
+  if (!g->kf_xy && !g->kf_yt && !g->kf_xt && !g->sparse) return 0;
+  BinPlan pl;
+  NVP_CHECK(binws != nullptr && plan_bins(d, tab, n, &pl), "binned grid path not available for this configuration");
+  if (g->kf_xy || g->kf_yt || g->kf_xt) {
+    BinArgs b{};
+    fill_bin_args(pl, tab, coords, n, binws, &b);
+    b.gkf[0] = g->kf_xy; b.gkf[1] = g->kf_yt; b.gkf[2] = g->kf_xt;
+    b.z16t = const_cast<uint8_t*>(dz16t); b.kz = kz;
+    b.scale = scale; b.scale_ptr = scale_ptr;
+    ScopedKernelTimer timer(K_SCATTER, st);
+    if (int rc = launch_binned<true>(d->n_features, pl, b, st)) return rc;
+    NVP_LAUNCH_CHECK();
+  }
+  if (g->sparse == nullptr) return 0;
+  nvp_grads gs{};
+  gs.sparse = g->sparse;   // voxel neighbourhood only: the direct kernel with the keyframe planes switched off
+  GridArgs a{};
+  a.tab = tab; a.coords = coords; a.n = n;
+  a.gsparse = gs.sparse;
+  a.dz16t = dz16t; a.kz = kz;
+  a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
+  a.scale = scale; a.scale_ptr = scale_ptr;
+  a.lvl_begin = tab.n_levels;
+  return dispatch(true, d->n_features, d->sparse_features, a, st);
+}
+
 
 }  // namespace nvp

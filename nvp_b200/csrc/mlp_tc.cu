@@ -1038,6 +1038,7 @@ struct TcWorkspace {
   uint8_t* dz16t;
   float* rgb;
   float* gscale;
+  void* binws;     // bucket state of the binned grid path (NULL: direct grid kernels)
   size_t total;
 };
 TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
@@ -1054,6 +1055,12 @@ TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
   w.wpk_bwd = take(static_cast<size_t>(8) * kPanelBytes + static_cast<size_t>(6) * m.ZP * 128);
   w.z16t = take(static_cast<size_t>(tiles) * m.KZ * kPanelBytes);
   w.rgb = reinterpret_cast<float*>(take(static_cast<size_t>(tiles) * kTile * 3 * sizeof(float)));
+  {
+    LevelTab tab;
+    size_t bin_bytes = 0;
+    if (build_level_table(d, &tab, nullptr) == 0) bin_bytes = grid_bin_workspace_bytes(d, tab, n);
+    w.binws = bin_bytes ? take(bin_bytes) : nullptr;
+  }
   if (what == 1) {
     w.stash = take(static_cast<size_t>(tiles) * SL_COUNT * 2 * kPanelBytes);
     w.dpre = take(static_cast<size_t>(tiles) * DP_COUNT * 2 * kPanelBytes);
@@ -1123,7 +1130,12 @@ int tc_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   const Dims m = make_dims(d);
   int rc;
   if ((rc = pack_forward_weights(d, p, w.wpk_fwd, nullptr, st))) return rc;
-  if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st, temporal_interp))) return rc;
+  if (w.binws) {
+    if ((rc = launch_grid_bin(d, tab, coords, n, m.KZ, w.binws, st))) return rc;
+    if ((rc = launch_grid_gather_binned(d, tab, p, coords, n, w.z16t, m.KZ, w.binws, st, temporal_interp))) return rc;
+  } else if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st, temporal_interp))) {
+    return rc;
+  }
   return launch_forward(d, p, w, tsteps, n, out_rgb, false, st);
 }
 
@@ -1159,7 +1171,12 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   if ((rc = pack_forward_weights(d, p, w.wpk_fwd, &b, st, w.wpk_bwd))) return rc;
 
   // 3. positional features, 4. fused forward (keeps the activation stash)
-  if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st))) return rc;
+  if (w.binws) {
+    if ((rc = launch_grid_bin(d, tab, coords, n, m.KZ, w.binws, st))) return rc;
+    if ((rc = launch_grid_gather_binned(d, tab, p, coords, n, w.z16t, m.KZ, w.binws, st))) return rc;
+  } else if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st))) {
+    return rc;
+  }
   float* rgb = out_rgb ? out_rgb : w.rgb;
   if ((rc = launch_forward(d, p, w, tsteps, n, rgb, true, st))) return rc;
 
@@ -1204,6 +1221,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   }
 
   // 7. scatter-add into the grids (dz is still multiplied by gs)
+  if (w.binws) return launch_grid_scatter_binned(d, tab, coords, n, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, w.binws, st);
   return launch_grid_scatter(d, tab, coords, n, nullptr, 0, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, st);
 }
 
