@@ -585,36 +585,13 @@ __global__ void __launch_bounds__(kCoarseGatherThreads) gather_coarse_kernel(con
   }
 }
 
-template <int F2, int F3>
-__global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArgs a) {
-  __shared__ float s_scale[NVP_MAX_LEVELS];
-  __shared__ int s_res[NVP_MAX_LEVELS];
-  __shared__ int s_off[NVP_MAX_LEVELS];
-  const int L = a.tab.n_levels;
-  if (threadIdx.x < L) {
-    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
-    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
-    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
-  }
-  __syncthreads();
-  const int64_t s = static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x;
-  if (s >= a.n_pad) return;
-  constexpr int LPC = 8 / F2;
-  const int cpp = L / LPC;                        // chunks per plane
-  const int fine_per_plane = cpp - a.n_coarse_chunks;
-  const int pass = blockIdx.y;
-  if (pass < 3 * fine_per_plane) {
-    // chunk-major so that consecutive passes reuse the same levels' working set size class; plane fastest
-    const int chunk = a.n_coarse_chunks + pass / 3, plane = pass % 3;
-    gather_chunk<F2>(a, s_scale, s_res, s_off, nullptr, 0, plane, chunk, s);
-    return;
-  }
-  // last pass: 3x3 neighbourhood of the nearest voxel + padding columns (constant 1 at column Z, then zeros),
-  // assembled in registers and written as whole 16-byte chunks (column 3*L*F2 is chunk aligned).
+// 3x3 neighbourhood of the nearest voxel + padding columns (constant 1 at column Z, then zeros) of one latent row,
+// assembled in registers and written as whole 16-byte chunks (c0 = first voxel column = 3*L*F2, chunk aligned).
+template <int F3>
+__device__ __forceinline__ void sparse_pad_sample(const GridArgs& a, int c0, int64_t s) {
   const int64_t tile = s >> 7;
   const int r = static_cast<int>(s & 127);
   uint8_t* tbase = a.z16t + tile * a.kz * tc::kPanelBytes;
-  const int c0 = 3 * L * F2;
   constexpr int NV = 9 * F3;                 // voxel features
   constexpr int NCH = (NV + 1 + 7) / 8;      // chunks holding features + the constant-1 column
   auto chunk_ptr = [&](int c) {
@@ -652,6 +629,33 @@ __global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArg
     }
   }
   for (int j = NCH; j < total_chunks; ++j) *chunk_ptr(c0 + 8 * j) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <int F2, int F3>
+__global__ void __launch_bounds__(kGridThreads) gather_fine_kernel(const GridArgs a) {
+  __shared__ float s_scale[NVP_MAX_LEVELS];
+  __shared__ int s_res[NVP_MAX_LEVELS];
+  __shared__ int s_off[NVP_MAX_LEVELS];
+  const int L = a.tab.n_levels;
+  if (threadIdx.x < L) {
+    s_scale[threadIdx.x] = a.tab.scale[threadIdx.x];
+    s_res[threadIdx.x] = a.tab.res[threadIdx.x];
+    s_off[threadIdx.x] = a.tab.offset[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x;
+  if (s >= a.n_pad) return;
+  constexpr int LPC = 8 / F2;
+  const int cpp = L / LPC;                        // chunks per plane
+  const int fine_per_plane = cpp - a.n_coarse_chunks;
+  const int pass = blockIdx.y;
+  if (pass < 3 * fine_per_plane) {
+    // chunk-major so that consecutive passes reuse the same levels' working set size class; plane fastest
+    const int chunk = a.n_coarse_chunks + pass / 3, plane = pass % 3;
+    gather_chunk<F2>(a, s_scale, s_res, s_off, nullptr, 0, plane, chunk, s);
+    return;
+  }
+  sparse_pad_sample<F3>(a, 3 * L * F2, s);
 }
 
 template <int F2>
@@ -726,12 +730,63 @@ int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
   return 0;
 }
 
+#include "grid_halfs.cuh"
+
+// Voxel-neighbourhood scatter-add of the binned path: one thread per (sample, x-row of the 3x3 neighbourhood).  The three
+// voxels of a row are contiguous in memory (y fastest), so for F3 == 2 the row's 6 floats go out as one 16-byte and
+// one 8-byte reduction (2 instead of 3 lane-level reductions).  idx = 3 * sample + row.
+template <int F3>
+__device__ __forceinline__ void sparse_scatter_row(const GridArgs& a, int col0, float scale, int64_t idx) {
+  const int64_t s = idx / 3;
+  const int i = static_cast<int>(idx - s * 3);   // row offset + 1
+  const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
+  const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
+  const int cx = min(max(vx + i - 1, 0), a.xres - 1);
+  const uint8_t* tb = a.dz16t + (s >> 7) * a.kz * tc::kPanelBytes;
+  const int r = static_cast<int>(s & 127);
+  float d[3][F3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = col0 + (i * 3 + j) * F3;
+    RawHalfs<F3> q = ld_halfs_raw<F3>(tb + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63));
+    cvt_halfs<F3>(q, d[j]);
+#pragma unroll
+    for (int f = 0; f < F3; ++f) d[j][f] *= scale;
+  }
+  float* row = a.gsparse + (static_cast<size_t>(vt) * a.xres + cx) * a.yres * F3;
+  if (F3 == 2 && vy >= 1 && vy + 1 < a.yres) {
+    float* p0 = row + static_cast<size_t>(vy - 1) * 2;
+    if ((reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
+      atomicAdd(reinterpret_cast<float4*>(p0), make_float4(d[0][0], d[0][1], d[1][0], d[1][1]));
+      atomicAdd(reinterpret_cast<float2*>(p0 + 4), make_float2(d[2][0], d[2][1]));
+    } else {
+      atomicAdd(reinterpret_cast<float2*>(p0), make_float2(d[0][0], d[0][1]));
+      atomicAdd(reinterpret_cast<float4*>(p0 + 2), make_float4(d[1][0], d[1][1], d[2][0], d[2][1]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int cy = min(max(vy + j - 1, 0), a.yres - 1);
+      red_feat<F3>(row + static_cast<size_t>(cy) * F3, d[j]);
+    }
+  }
+}
+
+template <int F3>
+__global__ void __launch_bounds__(256) sparse_scatter_rows_kernel(const GridArgs a, int col0) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= 3 * a.n) return;
+  const float scale = a.scale_ptr ? a.scale * __ldg(a.scale_ptr) : a.scale;
+  sparse_scatter_row<F3>(a, col0, scale, idx);
+}
+
 #include "grid_binned.cuh"
 
 // ---- host side of the binned path -----------------------------------------------------------
 struct BinPlan {
   BinTab bt;
-  int warps;            // warps (= private regions) per CTA
+  int warps;            // window warps (= private regions) per CTA
+  int sp_warps;         // extra warps per CTA running the voxel-neighbourhood role (0: separate kernels)
   size_t smem;          // dynamic shared memory per CTA
   int max_tasks;
   size_t o_cnt, o_offs, o_cursor, o_ntasks, o_zeros, o_tasks, o_recs, total;   // workspace byte offsets
@@ -743,13 +798,16 @@ int env_int(const char* name, int dflt) {
 }
 
 // false: this configuration does not use the binned path (the direct kernels serve it).
-bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl) {
+// `scatter` selects the launch shape of the scatter-add kernel (its register footprint is larger); tile size, chunking and
+// the workspace layout do not depend on it.
+bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl, bool scatter = false) {
   const int L = tab.n_levels, F2 = d->n_features;
   if (env_int("NVP_GRID_BINNED", 1) == 0) return false;
   // 32-bit row offsets into the latent tile buffer (<= 4 panels per 128-sample tile) and 32-bit bucket positions
   if ((L * F2) % 8 != 0 || n < 1 || n > 8000000) return false;
   constexpr size_t kRegionBudget = 216 * 1024;
   const int forced_tb = env_int("NVP_BIN_TB", 0);
+  const int want_warps = 20;   // a tile size qualifies when this many private windows fit one SM
   BinTab bt{};
   int warps = 0;
   for (int tb = 32; tb <= 128; tb <<= 1) {   // 3 * tb^2 counters must fit the scan kernel's shared memory
@@ -770,18 +828,22 @@ bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl) {
     bt.log_tb = 0;
     while ((1 << bt.log_tb) < tb) ++bt.log_tb;
     const size_t region = (static_cast<size_t>((base * F2 + 3) & ~3) + kStageFloats) * sizeof(float);   // + batch stage
-    warps = static_cast<int>(std::min<size_t>(kBinThreadsMax / 32, kRegionBudget / region));
-    if (warps >= kBinThreadsMax / 32 || forced_tb) break;
-    warps = 0;
+    warps = static_cast<int>(kRegionBudget / region);
+    if (warps >= want_warps || forced_tb || tb == 128) break;
   }
   if (warps < 1) return false;
-  warps = std::max(1, std::min(warps, env_int("NVP_BIN_WARPS", warps)));
+  // measured on config S (B200): gather 28 window + 4 voxel warps, scatter-add 22 + 2
+  int sp_warps = (d->sparse_features == F2 && F2 <= 4) ? env_int(scatter ? "NVP_BIN_SPARSE_WARPS_S" : "NVP_BIN_SPARSE_WARPS_G", scatter ? 2 : 4) : 0;
+  sp_warps = std::max(0, std::min(sp_warps, kBinThreadsMax / 32 - 1));
+  warps = std::max(1, std::min(std::min(warps, kBinThreadsMax / 32 - sp_warps),
+                               env_int(scatter ? "NVP_BIN_WARPS_S" : "NVP_BIN_WARPS_G", scatter ? 22 : 28)));
   const int64_t avg = (n + bt.nt - 1) / bt.nt;
   int chunk = env_int("NVP_BIN_CHUNK", 0);
   if (chunk <= 0) chunk = static_cast<int>(std::min<int64_t>(1 << 20, std::max<int64_t>(128, 2 * avg)));
   bt.chunk = (chunk + 31) / 32 * 32;
   pl->bt = bt;
   pl->warps = warps;
+  pl->sp_warps = sp_warps;
   pl->smem = static_cast<size_t>(warps) * (static_cast<size_t>((bt.base[L] * F2 + 3) & ~3) + kStageFloats) * sizeof(float);
   pl->max_tasks = static_cast<int>(3 * static_cast<int64_t>(bt.nt) + 3 * n / bt.chunk + 8);
   size_t off = 0;
@@ -816,13 +878,22 @@ int device_sms() {
   return sms;
 }
 
+template <int F2, bool SCATTER, int THREADS>
+int launch_binned_variant(const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
+  NVP_CUDA(cudaFuncSetAttribute(grid_binned_kernel<F2, SCATTER, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(pl.smem)));
+  const int blocks = a.sp_warps > 0 ? device_sms()
+                                    : std::max(1, std::min(device_sms(), (pl.max_tasks + pl.warps - 1) / pl.warps));
+  grid_binned_kernel<F2, SCATTER, THREADS><<<blocks, (pl.warps + a.sp_warps) * 32, pl.smem, st>>>(a);
+  return 0;
+}
 template <int F2, bool SCATTER>
 int launch_binned_kernel(const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
-  NVP_CUDA(cudaFuncSetAttribute(grid_binned_kernel<F2, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(pl.smem)));
-  const int blocks = std::max(1, std::min(device_sms(), (pl.max_tasks + pl.warps - 1) / pl.warps));
-  grid_binned_kernel<F2, SCATTER><<<blocks, pl.warps * 32, pl.smem, st>>>(a);
-  return 0;
+  // the register budget of a variant follows from its thread bound (64 K registers per SM)
+  const int warps = pl.warps + a.sp_warps;
+  if (warps <= 16) return launch_binned_variant<F2, SCATTER, 512>(pl, a, st);
+  if (warps <= 24) return launch_binned_variant<F2, SCATTER, 768>(pl, a, st);
+  return launch_binned_variant<F2, SCATTER, 1024>(pl, a, st);
 }
 template <bool SCATTER>
 int launch_binned(int f2, const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
@@ -943,12 +1014,7 @@ int launch_grid_gather_binned(const nvp_desc* d, const LevelTab& tab, const nvp_
   fill_bin_args(pl, tab, coords, n, binws, &b);
   b.kf[0] = p->kf_xy; b.kf[1] = p->kf_yt; b.kf[2] = p->kf_xt;
   b.z16t = z16t; b.kz = kz;
-  {
-    ScopedKernelTimer timer(K_GATHER, st);
-    if (int rc = launch_binned<false>(d->n_features, pl, b, st)) return rc;
-    NVP_LAUNCH_CHECK();
-  }
-  // 3x3 voxel neighbourhood + padding columns (+ all-zero padding rows): the last pass of gather_fine_kernel
+  // 3x3 voxel neighbourhood + padding columns (+ all-zero padding rows)
   GridArgs a{};
   a.tab = tab; a.coords = coords; a.n = n;
   a.sparse = p->sparse;
@@ -956,8 +1022,16 @@ int launch_grid_gather_binned(const nvp_desc* d, const LevelTab& tab, const nvp_
   a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
   a.interp = temporal_interp ? 1 : 0;
   a.scale = 1.0f;
-  a.n_coarse_chunks = tab.n_levels * d->n_features / 8;   // no keyframe passes
+  a.n_coarse_chunks = tab.n_levels * d->n_features / 8;   // no keyframe passes in gather_fine_kernel
   a.zero_planes = 1;
+  b.sp = a; b.sp_col0 = 3 * tab.n_levels * d->n_features;
+  b.win_warps = pl.warps; b.sp_warps = pl.sp_warps;
+  {
+    ScopedKernelTimer timer(K_GATHER, st);
+    if (int rc = launch_binned<false>(d->n_features, pl, b, st)) return rc;
+    NVP_LAUNCH_CHECK();
+  }
+  if (pl.sp_warps > 0) return 0;
   dim3 grid(static_cast<unsigned>((a.n_pad + kGridThreads - 1) / kGridThreads), 1);
   ScopedKernelTimer timer(K_GATHER, st);
   switch (d->n_features * 16 + d->sparse_features) {
@@ -976,28 +1050,41 @@ int launch_grid_scatter_binned(const nvp_desc* d, const LevelTab& tab, const flo
                                void* binws, cudaStream_t st) {
   if (!g->kf_xy && !g->kf_yt && !g->kf_xt && !g->sparse) return 0;
   BinPlan pl;
-  NVP_CHECK(binws != nullptr && plan_bins(d, tab, n, &pl), "binned grid path not available for this configuration");
-  if (g->kf_xy || g->kf_yt || g->kf_xt) {
+  NVP_CHECK(binws != nullptr && plan_bins(d, tab, n, &pl, true), "binned grid path not available for this configuration");
+  GridArgs a{};
+  a.tab = tab; a.coords = coords; a.n = n;
+  a.gsparse = g->sparse;
+  a.dz16t = dz16t; a.kz = kz;
+  a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
+  a.scale = scale; a.scale_ptr = scale_ptr;
+  a.lvl_begin = tab.n_levels;
+  const bool any_kf = g->kf_xy || g->kf_yt || g->kf_xt;
+  if (any_kf) {
     BinArgs b{};
     fill_bin_args(pl, tab, coords, n, binws, &b);
     b.gkf[0] = g->kf_xy; b.gkf[1] = g->kf_yt; b.gkf[2] = g->kf_xt;
     b.z16t = const_cast<uint8_t*>(dz16t); b.kz = kz;
     b.scale = scale; b.scale_ptr = scale_ptr;
+    b.sp = a; b.sp_col0 = 3 * tab.n_levels * d->n_features;
+    b.win_warps = pl.warps; b.sp_warps = pl.sp_warps;
     ScopedKernelTimer timer(K_SCATTER, st);
     if (int rc = launch_binned<true>(d->n_features, pl, b, st)) return rc;
     NVP_LAUNCH_CHECK();
+    if (pl.sp_warps > 0) return 0;
   }
   if (g->sparse == nullptr) return 0;
-  nvp_grads gs{};
-  gs.sparse = g->sparse;   // voxel neighbourhood only: the direct kernel with the keyframe planes switched off
-  GridArgs a{};
-  a.tab = tab; a.coords = coords; a.n = n;
-  a.gsparse = gs.sparse;
-  a.dz16t = dz16t; a.kz = kz;
-  a.tres = d->t_resolution; a.xres = d->x_resolution; a.yres = d->y_resolution;
-  a.scale = scale; a.scale_ptr = scale_ptr;
-  a.lvl_begin = tab.n_levels;
-  return dispatch(true, d->n_features, d->sparse_features, a, st);
+  const int col0 = 3 * tab.n_levels * d->n_features;
+  const unsigned blocks = static_cast<unsigned>((3 * n + 255) / 256);
+  ScopedKernelTimer timer(K_SCATTER, st);
+  switch (d->sparse_features) {
+    case 1: sparse_scatter_rows_kernel<1><<<blocks, 256, 0, st>>>(a, col0); break;
+    case 2: sparse_scatter_rows_kernel<2><<<blocks, 256, 0, st>>>(a, col0); break;
+    case 4: sparse_scatter_rows_kernel<4><<<blocks, 256, 0, st>>>(a, col0); break;
+    case 8: sparse_scatter_rows_kernel<8><<<blocks, 256, 0, st>>>(a, col0); break;
+    default: NVP_CHECK(false, "3d n_features_per_level must be 1, 2, 4 or 8");
+  }
+  NVP_LAUNCH_CHECK();
+  return 0;
 }
 
 

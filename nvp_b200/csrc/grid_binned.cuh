@@ -49,9 +49,15 @@ struct BinArgs {
   float scale;
   const float* scale_ptr;
   const uint4* zeros;      // 16 zero bytes (source of padding entries' latent gradient)
+  // voxel-neighbourhood role: warps [win_warps, blockDim/32) of every CTA run the 3x3-voxel gather (+ padding
+  // columns) / scatter-add of grid.cu next to the window warps - DRAM-latency-bound work hidden under the
+  // shared-memory-bound window work.  sp_warps == 0: separate kernels do it.
+  GridArgs sp;
+  int sp_col0;             // first voxel column of the latent row (3 * L * F2)
+  int win_warps, sp_warps;
 };
 
-constexpr int kBinThreadsMax = 512;
+constexpr int kBinThreadsMax = 1024;   // kernel variants are compiled for 512 / 768 / 1024 threads per CTA
 
 // One bucket entry: byte offset of the sample's latent row inside the tile buffer (0xffffffff = padding entry of a
 // partial batch), the row's swizzle term ((row & 7) << 4) and the sample's two plane coordinates.
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(1024) grid_bin_scan_kernel(const BinArgs a) {
   const int m = 3 * a.bt.nt;
   for (int i = threadIdx.x; i < m; i += 1024) s_cnt[i] = a.cnt[i];
   __syncthreads();
-  const int per = (m + 1023) / 1024;
+  const int per = ((m + 1023) / 1024) | 1;   // odd run length: the threads' strided walks hit distinct banks
   const int i0 = min(m, static_cast<int>(threadIdx.x) * per), i1 = min(m, i0 + per);
   int csum = 0, tsum = 0;
   for (int i = i0; i < i1; ++i) {
@@ -162,52 +168,6 @@ __device__ __forceinline__ void sts_feat(float* p, const float (&v)[F]) {
   }
 }
 
-// F consecutive halfs (one level of one plane) of a latent row in the MMA tile format; never straddles a 16-byte chunk
-// because F divides 8 and the column is a multiple of F.  The load returns the raw bits (so that a prefetch does not
-// wait for the data); cvt_halfs converts at the point of use.
-template <int F> struct RawHalfs { uint32_t w[(F + 1) / 2]; };
-template <int F>
-__device__ __forceinline__ RawHalfs<F> ld_halfs_raw(const uint8_t* p) {
-  RawHalfs<F> q;
-  if constexpr (F == 1) {
-    q.w[0] = __ldg(reinterpret_cast<const unsigned short*>(p));
-  } else if constexpr (F == 2) {
-    q.w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
-  } else if constexpr (F == 4) {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-    q.w[0] = t.x; q.w[1] = t.y;
-  } else {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
-    q.w[0] = t.x; q.w[1] = t.y; q.w[2] = t.z; q.w[3] = t.w;
-  }
-  return q;
-}
-template <int F>
-__device__ __forceinline__ void cvt_halfs(const RawHalfs<F>& q, float (&v)[F]) {
-  if constexpr (F == 1) {
-    v[0] = __half2float(__ushort_as_half(static_cast<unsigned short>(q.w[0])));
-  } else {
-#pragma unroll
-    for (int i = 0; i < F / 2; ++i) {
-      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&q.w[i]));
-      v[2 * i] = t.x; v[2 * i + 1] = t.y;
-    }
-  }
-}
-template <int F>
-__device__ __forceinline__ void st_halfs(uint8_t* p, const float (&v)[F]) {
-  if constexpr (F == 1) {
-    *reinterpret_cast<__half*>(p) = __float2half_rn(v[0]);
-  } else if constexpr (F == 2) {
-    *reinterpret_cast<uint32_t*>(p) = tc::pack_half2(v[0], v[1]);
-  } else if constexpr (F == 4) {
-    *reinterpret_cast<uint2*>(p) = make_uint2(tc::pack_half2(v[0], v[1]), tc::pack_half2(v[2], v[3]));
-  } else {
-    *reinterpret_cast<uint4*>(p) = make_uint4(tc::pack_half2(v[0], v[1]), tc::pack_half2(v[2], v[3]),
-                                              tc::pack_half2(v[4], v[5]), tc::pack_half2(v[6], v[7]));
-  }
-}
-
 // Rare path (plane coordinates outside [0,1], i.e. cells outside the task's window): the direct global access of the
 // unbinned kernels.  Out of line to keep the hot loops small.
 template <int F2> struct CornerPair { float a[F2], b[F2]; };
@@ -277,8 +237,8 @@ __device__ __forceinline__ void region_io(float* __restrict__ reg, const float* 
   }
 }
 
-template <int F2, bool SCATTER>
-__global__ void __launch_bounds__(kBinThreadsMax, 1) grid_binned_kernel(const BinArgs a) {
+template <int F2, bool SCATTER, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a) {
   extern __shared__ __align__(16) float s_region[];
   __shared__ float s_scale[NVP_MAX_LEVELS];
   __shared__ int s_res[NVP_MAX_LEVELS], s_off[NVP_MAX_LEVELS], s_E[NVP_MAX_LEVELS], s_base[NVP_MAX_LEVELS + 1];
@@ -294,7 +254,24 @@ __global__ void __launch_bounds__(kBinThreadsMax, 1) grid_binned_kernel(const Bi
   if (threadIdx.x <= L) s_base[threadIdx.x] = a.bt.base[threadIdx.x];
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = a.win_warps;
+  if (warp >= nwarps) {
+    if constexpr (F2 <= 4) {   // (the role is only enabled when the 3-D grid has F2 features per voxel)
+      const int64_t gtid = (static_cast<int64_t>(blockIdx.x) * a.sp_warps + (warp - nwarps)) * 32 + lane;
+      const int64_t gstride = static_cast<int64_t>(gridDim.x) * a.sp_warps * 32;
+      if constexpr (SCATTER) {
+        if (a.sp.gsparse != nullptr) {
+          const float sscale = a.sp.scale_ptr ? a.sp.scale * __ldg(a.sp.scale_ptr) : a.sp.scale;
+#pragma unroll 2
+          for (int64_t idx = gtid; idx < 3 * a.sp.n; idx += gstride) sparse_scatter_row<F2>(a.sp, a.sp_col0, sscale, idx);
+        }
+      } else {
+#pragma unroll 2
+        for (int64_t s = gtid; s < a.sp.n_pad; s += gstride) sparse_pad_sample<F2>(a.sp, a.sp_col0, s);
+      }
+    }
+    return;
+  }
   const int region_floats = (a.bt.base[L] * F2 + 3) & ~3;
   float* reg = s_region + static_cast<size_t>(warp) * (region_floats + kStageFloats);
   StagedSample* stage = reinterpret_cast<StagedSample*>(reg + region_floats);
