@@ -249,7 +249,6 @@ def run_ours(args):
         c, t, g = synth_batch(n, 1000 * rank + i, t_range)
         host.append((c.pin_memory(), t.pin_memory(), g.pin_memory()))
     resident = [(c.to(dev), t.to(dev), g.to(dev)) for c, t, g in host]
-    stage = (torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1]), torch.empty_like(resident[0][2]))
     loss_sum = torch.zeros(1, device=dev)
     launches = [0]
 
@@ -294,16 +293,31 @@ def run_ours(args):
     loss_last = float(loss_sum) / (3.0 * n)
 
     # ---- end-to-end through the public API with host buffers
+    # every step's inputs start in pinned HOST memory; nvp_b200.dataio.DevicePrefetcher (the loop a user of
+    # training.train gets) copies batch i+1 on a side stream while step i computes.  All K copies, K steps and K
+    # loss read-backs happen inside the timed region; the first copy is not overlapped with anything.
+    from nvp_b200.dataio import DevicePrefetcher
+
+    def host_batches():
+        i = 0
+        while True:
+            yield host[i % n_pool]
+            i += 1
+
+    pf_box = [None]
+
     def e2e_step(i):
-        c, t, g = host[i % n_pool]
-        stage[0].copy_(c, non_blocking=True)
-        stage[1].copy_(t, non_blocking=True)
-        stage[2].copy_(g, non_blocking=True)
-        step(*stage)
+        if pf_box[0] is None:
+            pf_box[0] = DevicePrefetcher(host_batches(), device=dev)
+        batch = next(pf_box[0])
+        step(*batch)
+        pf_box[0].release()
         _ = loss_sum.item()          # D2H read of the step's result
 
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
+    torch.cuda.synchronize()
+    pf_box[0] = None                 # the timed loop starts with nothing prefetched
     ms_e2e = timed(e2e_step, args.steps)
     # keep the clock sampler fed for at least ~1.5 s of the same loop (short --steps runs give NVML no samples)
     t_end = time.time() + max(0.0, 1.5 - (ms_total + ms_e2e) / 1e3)

@@ -87,10 +87,16 @@ __global__ void __launch_bounds__(256) grid_bin_count_kernel(const BinArgs a) {
 // task list itself.  A bucket of c samples becomes ceil(c / chunk) tasks.  The counters are staged in shared memory
 // with coalesced reads; each thread then owns a contiguous run of buckets.
 __global__ void __launch_bounds__(1024) grid_bin_scan_kernel(const BinArgs a) {
-  extern __shared__ int s_cnt[];   // [3 * nt]
+  extern __shared__ __align__(16) int s_cnt[];   // [3 * nt]
   __shared__ int s_c[1024], s_t[1024];
   const int m = 3 * a.bt.nt;
-  for (int i = threadIdx.x; i < m; i += 1024) s_cnt[i] = a.cnt[i];
+  {
+    // coalesced 16-byte loads, several in flight per thread (m = 3 * tb^2 is a multiple of 4)
+    const int4* src = reinterpret_cast<const int4*>(a.cnt);
+    int4* dst = reinterpret_cast<int4*>(s_cnt);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < m / 4; i += 1024) dst[i] = __ldg(src + i);
+  }
   __syncthreads();
   const int per = ((m + 1023) / 1024) | 1;   // odd run length: the threads' strided walks hit distinct banks
   const int i0 = min(m, static_cast<int>(threadIdx.x) * per), i1 = min(m, i0 + per);
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(1024) grid_bin_scan_kernel(const BinArgs a) {
   for (int i = i0; i < i1; ++i) {
     const int c = s_cnt[i];
     csum += c;
-    tsum += (c + a.bt.chunk - 1) / a.bt.chunk;
+    tsum += c == 0 ? 0 : (c <= a.bt.chunk ? 1 : (c + a.bt.chunk - 1) / a.bt.chunk);
   }
   s_c[threadIdx.x] = csum; s_t[threadIdx.x] = tsum;
   __syncthreads();
@@ -116,7 +122,13 @@ __global__ void __launch_bounds__(1024) grid_bin_scan_kernel(const BinArgs a) {
     co += c;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < m; i += 1024) { const int o = s_cnt[i]; a.offs[i] = o; a.cursor[i] = o; }
+  {
+    int4* o4 = reinterpret_cast<int4*>(a.offs);
+    int4* c4 = reinterpret_cast<int4*>(a.cursor);
+    const int4* s4 = reinterpret_cast<const int4*>(s_cnt);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < m / 4; i += 1024) { const int4 o = s4[i]; o4[i] = o; c4[i] = o; }
+  }
   if (threadIdx.x == 1023) { a.offs[m] = s_c[1023]; a.n_tasks[0] = s_t[1023]; }
 }
 

@@ -136,3 +136,68 @@ class DeviceSampler:
         t_idx = t_idx.to(self.device, torch.int64).contiguous()
         p_idx = p_idx.to(self.device, torch.int64).contiguous()
         return self._run(t_idx.numel(), t_idx, p_idx, 0)
+
+
+class DevicePrefetcher:
+    """Host -> device double buffering for the training loop (replaces the reference's per-step `.cuda()` copies,
+    training.py:45-46): batch i+1 is copied from pinned host memory on a side stream while step i computes.
+
+        pf = DevicePrefetcher(iterable_of_host_batches)          # each batch: tuple of CPU tensors
+        for dev_batch in pf: step(*dev_batch)
+
+    The consumer's stream waits on the copy's event before using a slot, and a slot is only overwritten after the
+    step that read it has been enqueued and recorded, so no host synchronisation is needed beyond the caller's own.
+    """
+
+    def __init__(self, batches, device="cuda", depth=2):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self.slots = [None] * depth
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [None] * depth
+        self.head = 0       # next slot to fill
+        self.tail = 0       # next slot to hand out
+        self.inflight = 0
+
+    def _fill(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            return False
+        k = self.head
+        with torch.cuda.stream(self.copy_stream):
+            if self.done[k] is not None:
+                self.copy_stream.wait_event(self.done[k])      # the step that read this slot has finished
+            if self.slots[k] is None:
+                self.slots[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
+            for dst, src in zip(self.slots[k], host):
+                dst.copy_(src if src.is_pinned() else src.pin_memory(), non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.head = (k + 1) % self.depth
+        self.inflight += 1
+        return True
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        while self.inflight < self.depth - 1 and self._fill():
+            pass
+        if self.inflight == 0 and not self._fill():
+            raise StopIteration
+        k = self.tail
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[k])
+        self._fill()                                           # next batch's copy overlaps this step
+        self.tail = (k + 1) % self.depth
+        self.inflight -= 1
+        self._pending = k
+        return self.slots[k]
+
+    def release(self):
+        """Call after enqueueing the step that consumes the batch last returned."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.done[self._pending] = ev

@@ -47,3 +47,25 @@ def test_throughput_mode_is_uniform_deterministic_and_consistent():
     assert torch.equal(x["all_coords"][0, :, 0].cpu(), torch.linspace(0, 1, T)[ti])
     assert torch.equal(x["temporal_steps"][0].cpu(), torch.linspace(0.5 / T, 1 - 0.5 / T, T)[ti])
     assert torch.equal(y["img"][0].cpu(), torch.from_numpy(vid).view(T, -1, 3)[ti, pi])
+
+
+def test_device_prefetcher_preserves_order_and_content():
+    """Double-buffered H2D staging: batches arrive in order, bit-identical, while a consumer kernel is still running on
+    the previous slot (the consumer below is slow on purpose)."""
+    from nvp_b200.dataio import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = [(torch.rand(50000, 3, generator=g).pin_memory(), torch.randint(0, 255, (50000, 3), generator=g, dtype=torch.uint8))
+            for _ in range(7)]
+    pf = DevicePrefetcher(iter(host), device="cuda")
+    sums, seen = [], 0
+    for i, (c, u) in enumerate(pf):
+        acc = c.double().sum() + u.double().sum()
+        for _ in range(20):
+            acc = acc + (c.double() * 1e-9).sum()      # keep the slot busy
+        sums.append(acc)
+        pf.release()
+        seen += 1
+    assert seen == len(host)
+    for (c, u), got in zip(host, sums):
+        ref = c.double().sum() + u.double().sum() + 20 * (c.double() * 1e-9).sum()
+        assert abs(float(got) - float(ref)) <= 1e-6 * abs(float(ref))
