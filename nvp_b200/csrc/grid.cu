@@ -832,11 +832,11 @@ bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl, b
     if (warps >= want_warps || forced_tb || tb == 128) break;
   }
   if (warps < 1) return false;
-  // measured on config S (B200): gather 28 window + 4 voxel warps, scatter-add 22 + 2
+  // measured on config S (B200): gather 20 window + 4 voxel warps, scatter-add 22 + 2
   int sp_warps = (d->sparse_features == F2 && F2 <= 4) ? env_int(scatter ? "NVP_BIN_SPARSE_WARPS_S" : "NVP_BIN_SPARSE_WARPS_G", scatter ? 2 : 4) : 0;
   sp_warps = std::max(0, std::min(sp_warps, kBinThreadsMax / 32 - 1));
   warps = std::max(1, std::min(std::min(warps, kBinThreadsMax / 32 - sp_warps),
-                               env_int(scatter ? "NVP_BIN_WARPS_S" : "NVP_BIN_WARPS_G", scatter ? 22 : 28)));
+                               env_int(scatter ? "NVP_BIN_WARPS_S" : "NVP_BIN_WARPS_G", scatter ? 22 : 20)));
   const int64_t avg = (n + bt.nt - 1) / bt.nt;
   int chunk = env_int("NVP_BIN_CHUNK", 0);
   if (chunk <= 0) chunk = static_cast<int>(std::min<int64_t>(1 << 20, std::max<int64_t>(128, 2 * avg)));

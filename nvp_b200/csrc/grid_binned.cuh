@@ -62,7 +62,11 @@ constexpr int kBinThreadsMax = 1024;   // kernel variants are compiled for 512 /
 // One bucket entry: byte offset of the sample's latent row inside the tile buffer (0xffffffff = padding entry of a
 // partial batch), the row's swizzle term ((row & 7) << 4) and the sample's two plane coordinates.
 struct __align__(16) StagedSample { uint32_t rowoff, swz; float u0, u1; };
-constexpr int kStageFloats = 32 * sizeof(StagedSample) / sizeof(float);
+// Per-warp scratch behind the window region: the scatter-add's staged batch (32 x 16 B) or the gather's per-task level
+// table (n_levels <= 32 x 32 B).
+struct __align__(16) LevelWindow { float scale; int lo0, lo1, base; int E, amax0, amax1, res; };
+constexpr int kStageFloats = NVP_MAX_LEVELS * sizeof(LevelWindow) / sizeof(float);
+static_assert(kStageFloats * sizeof(float) >= 32 * sizeof(StagedSample), "stage too small");
 
 __device__ __forceinline__ int bin_tile_axis(float u, int tb) {
   const int b = __float2int_rz(u * static_cast<float>(tb));   // tb is a power of two: the product is exact
@@ -307,7 +311,79 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
     const uint8_t* zero_src = reinterpret_cast<const uint8_t*>(a.zeros);
     const uint4 pad_rec = make_uint4(0xffffffffu, 0u, __float_as_uint(ub0), __float_as_uint(ub1));
 
-    for (int lb = 0; lb < L; lb += 16) {
+    if constexpr (!SCATTER) {
+      // ---- gather: lane = sample.  Every lane walks the levels itself (4 corner reads per level from the warp's
+      // window), so the per-sample overhead (record, addressing, output row) is paid once per 32 samples and a
+      // latent row leaves as whole 16-byte chunks.  Same corner order / fma chain as the direct kernel.
+      LevelWindow* lw = reinterpret_cast<LevelWindow*>(stage);
+      if (lane < L) {
+        LevelWindow q;
+        q.scale = s_scale[lane]; q.res = s_res[lane]; q.E = s_E[lane];
+        q.lo0 = static_cast<int>(floorf(fmaf(q.scale, ub0, 0.5f)));
+        q.lo1 = static_cast<int>(floorf(fmaf(q.scale, ub1, 0.5f)));
+        q.base = s_base[lane] * F2;
+        q.amax0 = min(q.E - 2, q.res - 1 - q.lo0); q.amax1 = min(q.E - 2, q.res - 1 - q.lo1);
+        lw[lane] = q;
+      }
+      region_io<F2, REGION_LOAD>(reg, kfp, nullptr, s_scale, s_res, s_off, s_E, s_base, s_magic, 0, L, ub0, ub1, 1.0f, lane);
+      cp_async_wait_all();
+      __syncwarp();
+      constexpr int LPC = 8 / F2;                       // levels per 16-byte chunk of the latent row
+      const int col0 = plane * pw;
+      uint4 rec = beg + lane < end ? __ldg(recs + beg + lane) : pad_rec;
+      for (int i = beg; i < end; i += 32) {
+        const uint4 cur = rec;
+        rec = i + 32 + lane < end ? __ldg(recs + i + 32 + lane) : pad_rec;
+        const float u0 = __uint_as_float(cur.z), u1 = __uint_as_float(cur.w);
+        const bool valid = cur.x != 0xffffffffu;
+        for (int ch = 0; ch < L / LPC; ++ch) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < LPC; ++j) {
+            const int l = ch * LPC + j;
+            const LevelWindow q = lw[l];
+            const float p0 = fmaf(q.scale, u0, 0.5f), p1 = fmaf(q.scale, u1, 0.5f);
+            const float f0 = floorf(p0), f1 = floorf(p1);
+            const int i0 = static_cast<int>(f0), i1 = static_cast<int>(f1);
+            const float w0 = p0 - f0, w1 = p1 - f1;
+            const int aa = i0 - q.lo0, bb = i1 - q.lo1;
+            float v00[F2], v10[F2], v01[F2], v11[F2];
+            if (static_cast<unsigned>(aa) <= static_cast<unsigned>(q.amax0) && static_cast<unsigned>(bb) <= static_cast<unsigned>(q.amax1)) {
+              const float* cp = reg + q.base + (bb * q.E + aa) * F2;
+              lds_feat<F2>(cp, v00);
+              lds_feat<F2>(cp + F2, v10);
+              lds_feat<F2>(cp + q.E * F2, v01);
+              lds_feat<F2>(cp + q.E * F2 + F2, v11);
+            } else {
+              const float* kfl = kfp + static_cast<size_t>(s_off[l]) * F2;
+              const CornerPair<F2> r0 = direct_corner_pair_load<F2>(kfl, i0 + i1 * q.res, q.res * q.res);
+              const CornerPair<F2> r1 = direct_corner_pair_load<F2>(kfl, i0 + (i1 + 1) * q.res, q.res * q.res);
+#pragma unroll
+              for (int f = 0; f < F2; ++f) { v00[f] = r0.a[f]; v10[f] = r0.b[f]; v01[f] = r1.a[f]; v11[f] = r1.b[f]; }
+            }
+            const float a0 = 1.0f - w0, a1 = 1.0f - w1;
+            const float k00 = a0 * a1, k10 = w0 * a1, k01 = a0 * w1, k11 = w0 * w1;
+#pragma unroll
+            for (int f = 0; f < F2; ++f) {
+              float r = k00 * v00[f];
+              r = fmaf(k10, v10[f], r);
+              r = fmaf(k01, v01[f], r);
+              r = fmaf(k11, v11[f], r);
+              o[j * F2 + f] = r;
+            }
+          }
+          if (valid) {
+            const int col = col0 + ch * 8;
+            uint8_t* dst = a.z16t + static_cast<size_t>(col >> 6) * tc::kPanelBytes + cur.x +
+                           ((static_cast<uint32_t>((col & 63) >> 3) << 4) ^ cur.y);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(tc::pack_half2(o[0], o[1]), tc::pack_half2(o[2], o[3]),
+                                                        tc::pack_half2(o[4], o[5]), tc::pack_half2(o[6], o[7]));
+          }
+        }
+      }
+      __syncwarp();   // the level table and the window are rewritten by the next task
+    } else for (int lb = 0; lb < L; lb += 16) {
+      // ---- scatter-add: lane = (level, cell row); one sample per step of the warp
       const int le = min(L, lb + 16);
       const bool lv = lb + (lane >> 1) < L;
       const int l = lv ? lb + (lane >> 1) : L - 1;
@@ -323,12 +399,9 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
       const uint32_t cc16 = static_cast<uint32_t>((col & 63) >> 3) << 4;
 
       uint4 rec = beg + lane < end ? __ldg(recs + beg + lane) : pad_rec;
-      if constexpr (SCATTER) {
+      {
         float4* r4 = reinterpret_cast<float4*>(reg);
         for (int i = lane; i < region_floats / 4; i += 32) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        region_io<F2, REGION_LOAD>(reg, kfp, nullptr, s_scale, s_res, s_off, s_E, s_base, s_magic, lb, le, ub0, ub1, 1.0f, lane);
-        cp_async_wait_all();
       }
       __syncwarp();
 
@@ -351,31 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
         rec = i + 32 + lane < end ? __ldg(recs + i + 32 + lane) : pad_rec;   // lands while this batch is processed
         const int cnt = min(32, end - i);
 
-        if constexpr (!SCATTER) {
-          for (int k0 = 0; k0 < cnt; k0 += 4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const StagedSample q = stage[k0 + j];
-              float ka, kb, va[F2], vb[F2];
-              int i0, i1, loc;
-              if (geometry(q, ka, kb, i0, i1, loc)) {
-                lds_feat<F2>(rl + loc, va);
-                lds_feat<F2>(rl + loc + F2, vb);
-              } else {
-                const CornerPair<F2> cp = direct_corner_pair_load<F2>(kfp + goff * F2, i0 + (i1 + c1) * res, cells);
-#pragma unroll
-                for (int f = 0; f < F2; ++f) { va[f] = cp.a[f]; vb[f] = cp.b[f]; }
-              }
-              float r[F2];
-#pragma unroll
-              for (int f = 0; f < F2; ++f) {
-                r[f] = fmaf(kb, vb[f], ka * va[f]);
-                r[f] += __shfl_xor_sync(0xffffffffu, r[f], 1);
-              }
-              if (c1 == 0 && lv && q.rowoff != 0xffffffffu) st_halfs<F2>(zb + q.rowoff + (cc16 ^ q.swz), r);
-            }
-          }
-        } else {
+        if constexpr (SCATTER) {
           // latent-gradient values are fetched (as raw bits) one group ahead of their use: two register buffers
           constexpr int G = F2 <= 2 ? 8 : (F2 == 4 ? 4 : 2);
           constexpr int NG = 32 / G;
