@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <initializer_list>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -139,6 +141,24 @@ __device__ __forceinline__ void store_row32(uint8_t* panel, int r, int c0, const
   }
 }
 
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[N]) {
+  if constexpr (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+// N (16 or 32) consecutive columns starting at panel column c0 (multiple of N) of row r, as fp16.
+template <int N>
+__device__ __forceinline__ void store_rown(uint8_t* panel, int r, int c0, const float (&v)[N]) {
+#pragma unroll
+  for (int j = 0; j < N / 8; ++j) {
+    uint4 q;
+    q.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+    q.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+    q.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+    q.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(panel + panel_chunk_offset(r, (c0 >> 3) + j)) = q;
+  }
+}
+
 // Stash slots per tile (train mode), each 2 panels = 32 KiB.
 enum { SL_H0 = 0, SL_A0, SL_H1, SL_A1, SL_S1, SL_C1, SL_H2, SL_S2, SL_C2, SL_COUNT };
 
@@ -172,7 +192,7 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage, bool stag
   s.c = o; if (train) o += 2 * kPanelBytes;
   s.ring = o; o += nstage * kPanelBytes;
   s.consts = o; o += (10 * H + 4) * 4;      // bm[3][H] bs[3][H] ws0[H] wl[3][H] bl[3]
-  s.rgbx = o; o += H * 3 * 4;               // partial rgb of the upper column sub-chunk
+  s.rgbx = o; o += 3 * H * 3 * 4;           // partial rgb of the other column slices (up to 3)
   s.bars = o; o += 64 * 8;
   s.total = o;
   return s;
@@ -187,8 +207,12 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int KZ, int nstage, bool stag
 //     leaves through cp.async.bulk (TMA) stores, one 16 KiB panel at a time.
 // STAGE_SC: stage the sin/cos stash tiles in shared memory for TMA bulk stores (needs 64 KiB); when the latent is too
 // wide for that (config L) they are written with per-lane 16-byte stores instead.
-template <bool TRAIN, bool STAGE_SC>
-__global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs a) {
+// EW = epilogue warps (8 or 16): each TMEM lane quarter is served by EW/4 warps, every warp owning CW = 256/EW columns of
+// the current 64-column panel.  The epilogue's instruction issue bounds this kernel (30 K warp instructions per tile);
+// 16 warps give the four schedulers four warps each to interleave instead of two.
+template <bool TRAIN, bool STAGE_SC, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdArgs a) {
+  constexpr int CW = 256 / EW;   // columns per warp inside a 64-column panel
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const FwdSmem L = fwd_smem_layout(a.KZ, a.nstage, TRAIN && STAGE_SC);
@@ -216,12 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < 3 * H; i += kThreads) {
+  for (int i = tid; i < 3 * H; i += 64 + EW * 32) {
     s_bm[i] = __ldg(a.mod_b[i / H] + (i % H));
     s_bs[i] = __ldg(a.siren_b[i / H] + (i % H)) * (i < H ? a.w0 : 1.0f);
     s_wl[i] = __ldg(a.last_w + i);
   }
-  for (int i = tid; i < H; i += kThreads) s_ws0[i] = __ldg(a.siren_w0 + i) * a.w0;
+  for (int i = tid; i < H; i += 64 + EW * 32) s_ws0[i] = __ldg(a.siren_w0 + i) * a.w0;
   if (tid < 3) s_bl[tid] = __ldg(a.last_b + tid);
   if (tid == 0) {
     for (int i = 0; i < a.nstage; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
   } else {
     // ================= epilogue warps =================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int sub = (warp - 2) >> 2;           // which 32-column half of the current 64-column panel
+    const int sub = (warp - 2) >> 2;           // which CW-column slice of the current 64-column panel
     const int r = quarter * 32 + lane;         // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const bool issuer = (tid == 64);
@@ -315,59 +339,60 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
         tcgen05_fence_after();
 #pragma unroll 1
         for (int p = 0; p < 2; ++p) {
-          const int pc = sub * 32;           // column inside panel p
+          const int pc = sub * CW;           // column inside panel p
           const int col = p * 64 + pc;       // column inside the layer
           if (TRAIN) {
             // staging buffers of this panel were handed to the TMA two phases ago; at most the newest group may be pending
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
           }
-          uint32_t vm[32];
-          tmem_ld32(acc_m + lane_base + col, vm);
-          float hv[32], av[32];
+          uint32_t vm[CW];
+          tmem_ldn<CW>(acc_m + lane_base + col, vm);
+          float hv[CW], av[CW];
           if (step == 0) {
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < CW; ++i) {
               hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[col + i]);
               av[i] = fast_sin(fmaf(tau, s_ws0[col + i], s_bs[col + i])) * hv[i];
             }
           } else {
-            uint32_t vs[32];
-            tmem_ld32(acc_s + lane_base + col, vs);
+            uint32_t vs[CW];
+            tmem_ldn<CW>(acc_s + lane_base + col, vs);
             tmem_ld_wait();
-            float sv[32], cv[32];
+            float sv[CW], cv[CW];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < CW; ++i) {
               hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[step * H + col + i]);
               const float sp = __uint_as_float(vs[i]) + s_bs[step * H + col + i];
               if (TRAIN) fast_sincos(sp, sv[i], cv[i]); else sv[i] = fast_sin(sp);
               av[i] = sv[i] * hv[i];
             }
             if (TRAIN && STAGE_SC) {
-              store_row32(sbuf + p * kPanelBytes, r, pc, sv);
-              store_row32(cbuf + p * kPanelBytes, r, pc, cv);
+              store_rown<CW>(sbuf + p * kPanelBytes, r, pc, sv);
+              store_rown<CW>(cbuf + p * kPanelBytes, r, pc, cv);
             } else if (TRAIN) {
-              store_row32(st_base + (static_cast<size_t>(step == 1 ? SL_S1 : SL_S2) * 2 + p) * kPanelBytes, r, pc, sv);
-              store_row32(st_base + (static_cast<size_t>(step == 1 ? SL_C1 : SL_C2) * 2 + p) * kPanelBytes, r, pc, cv);
+              store_rown<CW>(st_base + (static_cast<size_t>(step == 1 ? SL_S1 : SL_S2) * 2 + p) * kPanelBytes, r, pc, sv);
+              store_rown<CW>(st_base + (static_cast<size_t>(step == 1 ? SL_C1 : SL_C2) * 2 + p) * kPanelBytes, r, pc, cv);
             }
           }
-          if (step < 2 || TRAIN) store_row32(hbuf + p * kPanelBytes, r, pc, hv);
+          if (step < 2 || TRAIN) store_rown<CW>(hbuf + p * kPanelBytes, r, pc, hv);
           if (step < 2) {
-            store_row32(abuf + p * kPanelBytes, r, pc, av);
+            store_rown<CW>(abuf + p * kPanelBytes, r, pc, av);
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < CW; ++i) {
               rgb0 = fmaf(av[i], s_wl[col + i], rgb0);
               rgb1 = fmaf(av[i], s_wl[H + col + i], rgb1);
               rgb2 = fmaf(av[i], s_wl[2 * H + col + i], rgb2);
             }
-            if (p == 1 && sub == 1) { s_rgbx[r * 3] = rgb0; s_rgbx[r * 3 + 1] = rgb1; s_rgbx[r * 3 + 2] = rgb2; }
+            if (p == 1 && sub > 0) { float* x = s_rgbx + ((sub - 1) * H + r) * 3; x[0] = rgb0; x[1] = rgb1; x[2] = rgb2; }
           }
           fence_proxy_async_smem();   // st.shared operand / staging tiles -> visible to UMMA and TMA (async proxy)
           tcgen05_fence_before();
-          asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");
           if (issuer) {
+            mbar_arrive(&panel_done[step * 2 + p]);   // first: the MMA warp is on the critical path, the stash stores are not
             if (TRAIN) {
               auto put = [&](int slot, const uint8_t* src) {
                 bulk_s2g(st_base + (static_cast<size_t>(slot) * 2 + p) * kPanelBytes, src + p * kPanelBytes, kPanelBytes);
@@ -377,13 +402,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdArgs 
               else { put(SL_H2, hbuf); if (STAGE_SC) { put(SL_S2, sbuf); put(SL_C2, cbuf); } }
               bulk_commit();
             }
-            mbar_arrive(&panel_done[step * 2 + p]);
           }
         }
         if (step == 2 && sub == 0 && valid) {
-          a.rgb[s * 3] = rgb0 + s_rgbx[r * 3] + s_bl[0];
-          a.rgb[s * 3 + 1] = rgb1 + s_rgbx[r * 3 + 1] + s_bl[1];
-          a.rgb[s * 3 + 2] = rgb2 + s_rgbx[r * 3 + 2] + s_bl[2];
+#pragma unroll
+          for (int q = 0; q < EW / 4 - 1; ++q) {   // partial sums of the other column slices
+            rgb0 += s_rgbx[(q * H + r) * 3]; rgb1 += s_rgbx[(q * H + r) * 3 + 1]; rgb2 += s_rgbx[(q * H + r) * 3 + 2];
+          }
+          a.rgb[s * 3] = rgb0 + s_bl[0];
+          a.rgb[s * 3 + 1] = rgb1 + s_bl[1];
+          a.rgb[s * 3 + 2] = rgb2 + s_bl[2];
         }
       }
     }
@@ -712,6 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
           tcgen05_fence_before();
           asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
           if (issuer) {
+            mbar_arrive(&panel_done[p]);   // first: the MMA warp is on the critical path, the dpre stores are not
             auto put = [&](int slot, const uint8_t* src) {
               bulk_s2g(dp_base + (static_cast<size_t>(slot) * 2 + p) * kPanelBytes, src, kPanelBytes);
             };
@@ -719,7 +748,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_backward_kernel(const BwdArgs
             else if (step == 1) { put(DP_S1, bc); put(DP_M1, bh); }
             else put(DP_M0, bh);
             bulk_commit();
-            mbar_arrive(&panel_done[p]);
             if (p == 1) {
               // staging set 0 is free once the small reductions (the last MMAs reading it) have completed and its
               // bulk stores have been read: refill it for the next phase that uses it.
@@ -1103,16 +1131,23 @@ int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w,
   NVP_CHECK(a.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core path");
   const size_t smem = fwd_smem_layout(m.KZ, a.nstage, stage_sc).total + 1024;
   const int grid = std::min(a.n_tiles, num_sms());
+  static const int epi_warps = [] { const char* v = getenv("NVP_FWD_EPI_WARPS"); return (v && atoi(v) == 16) ? 16 : 8; }();   // measured: no difference (the kernel is latency-chain bound)
   ScopedKernelTimer timer(K_MLP_FWD, st);
-  auto launch = [&](auto kernel) -> int {
+  auto launch = [&](auto kernel, int threads) -> int {
     NVP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel<<<grid, kThreads, smem, st>>>(a);
+    kernel<<<grid, threads, smem, st>>>(a);
     return 0;
   };
   int rc;
-  if (!train) rc = launch(mlp_forward_kernel<false, false>);
-  else if (stage_sc) rc = launch(mlp_forward_kernel<true, true>);
-  else rc = launch(mlp_forward_kernel<true, false>);
+  if (epi_warps == 16) {
+    if (!train) rc = launch(mlp_forward_kernel<false, false, 16>, 576);
+    else if (stage_sc) rc = launch(mlp_forward_kernel<true, true, 16>, 576);
+    else rc = launch(mlp_forward_kernel<true, false, 16>, 576);
+  } else {
+    if (!train) rc = launch(mlp_forward_kernel<false, false, 8>, 320);
+    else if (stage_sc) rc = launch(mlp_forward_kernel<true, true, 8>, 320);
+    else rc = launch(mlp_forward_kernel<true, false, 8>, 320);
+  }
   if (rc) return rc;
   NVP_LAUNCH_CHECK();
   return 0;

@@ -10,9 +10,7 @@ m = nvp_b200.NVP(out_features=3, encoding_config=cfg, mode="tc").cuda()
 _, flat = flatten_parameters(m)
 c, t, g = [x.cuda() for x in bench.synth_batch(bench.N_SAMPLES, 0)]
 ls = torch.zeros(1, device="cuda")
-combos = [dict(), dict(NVP_BIN_WARPS_G="20", NVP_BIN_SPARSE_WARPS_G="4"), dict(NVP_BIN_WARPS_G="12", NVP_BIN_SPARSE_WARPS_G="4"),
-          dict(NVP_BIN_WARPS_G="24", NVP_BIN_SPARSE_WARPS_G="8"), dict(NVP_BIN_WARPS_G="16", NVP_BIN_SPARSE_WARPS_G="8"),
-          dict(NVP_BIN_TB="64", NVP_BIN_WARPS_G="12", NVP_BIN_SPARSE_WARPS_G="4")]
+combos = [dict()]
 KEYS = ("NVP_GRID_BINNED", "NVP_BIN_TB", "NVP_BIN_CHUNK", "NVP_BIN_WARPS_G", "NVP_BIN_WARPS_S", "NVP_BIN_SPARSE_WARPS_G", "NVP_BIN_SPARSE_WARPS_S")
 for combo in combos:
     for k in KEYS:
