@@ -132,9 +132,10 @@ def measured_peaks():
 
 def measured_traffic(config: str):
     """DRAM bytes per step and kernel kind from the committed `ncu --set full` capture of prof_step.py (same workload)."""
-    path = os.path.join(ROOT, "profiles", f"r01_traffic_{config}.json")
-    if os.path.isfile(path):
-        with open(path) as f:
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_traffic_{config}.json")))
+    if paths:
+        with open(paths[-1]) as f:           # newest capture (file names sort by round / session)
             return json.load(f)["dram_bytes_per_step"]
     return {}
 
