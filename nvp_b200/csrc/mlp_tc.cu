@@ -119,13 +119,19 @@ int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, B
 // ------------------------------------------------------------------------------------------
 // sin/cos with two-constant Cody-Waite reduction to [-pi, pi] then the SFU approximation
 // (abs err ~4e-7 after reduction; arguments reach |30*(w*t+b)| ~ 60, modulation.py:25,69).
+// XU = true rounds with the magic-number add on the FMA pipe instead of rintf (an FRND on the quarter-rate XU pipe): the
+// training epilogues are bound by that pipe (MUFU.SIN + MUFU.COS per element; measured -6 % forward time), while the
+// inference forward (one MUFU per element) is bound by the FMA pipe and keeps rintf.
+template <bool XU_BOUND>
 __device__ __forceinline__ float reduce_2pi(float x) {
-  const float k = rintf(x * 0.15915494309189535f);
+  const float y = x * 0.15915494309189535f;
+  const float k = XU_BOUND ? __fadd_rn(__fadd_rn(y, 12582912.0f), -12582912.0f) : rintf(y);   // magic: rint for |y| < 2^22
   float r = fmaf(k, -6.2831854820251465f, x);
   return fmaf(k, 1.7484556e-7f, r);
 }
-__device__ __forceinline__ float fast_sin(float x) { return __sinf(reduce_2pi(x)); }
-__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) { __sincosf(reduce_2pi(x), &s, &c); }
+template <bool XU_BOUND>
+__device__ __forceinline__ float fast_sin(float x) { return __sinf(reduce_2pi<XU_BOUND>(x)); }
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) { __sincosf(reduce_2pi<true>(x), &s, &c); }
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, 0.01f * x); }
 
 // Store 32 consecutive columns (starting at panel column c0, multiple of 32) of row r into a panel as fp16.
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
 #pragma unroll
             for (int i = 0; i < CW; ++i) {
               hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[col + i]);
-              av[i] = fast_sin(fmaf(tau, s_ws0[col + i], s_bs[col + i])) * hv[i];
+              av[i] = fast_sin<TRAIN>(fmaf(tau, s_ws0[col + i], s_bs[col + i])) * hv[i];
             }
           } else {
             uint32_t vs[CW];
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
             for (int i = 0; i < CW; ++i) {
               hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[step * H + col + i]);
               const float sp = __uint_as_float(vs[i]) + s_bs[step * H + col + i];
-              if (TRAIN) fast_sincos(sp, sv[i], cv[i]); else sv[i] = fast_sin(sp);
+              if (TRAIN) fast_sincos(sp, sv[i], cv[i]); else sv[i] = fast_sin<false>(sp);
               av[i] = sv[i] * hv[i];
             }
             if (TRAIN && STAGE_SC) {
