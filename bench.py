@@ -253,12 +253,20 @@ def run_ours(args):
     loss_sum = torch.zeros(1, device=dev)
     launches = [0]
 
+    overlap = None
+    if world > 1 and not args.no_overlap:
+        from nvp_b200.dist import GridFirstAllReduce, grid_grad_numel
+        overlap = GridFirstAllReduce(reduce_view, min(grid_grad_numel(model, flat), reduce_view.numel()))
+
     def step(c, t, g):
         flat.zero_()
         loss_sum.zero_()
-        model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum)
+        model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum,
+                           grid_event=overlap.event if overlap else None)
         launches[0] += functional.last_launch_count()
-        if world > 1:
+        if overlap:
+            overlap.run()            # grid gradients reduce on a side stream under the wgrad kernel, MLP gradients after it
+        elif world > 1:
             dist.all_reduce(reduce_view)
 
     def barrier():
@@ -336,8 +344,11 @@ def run_ours(args):
     def step_opt(i):
         c, t, g = resident[i % n_pool]
         loss_sum.zero_()
-        model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum)
-        if world > 1:
+        model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum,
+                           grid_event=overlap.event if overlap else None)
+        if overlap:
+            overlap.run()
+        elif world > 1:
             dist.all_reduce(reduce_view)
         fopt.step(zero_grad=True)
 
@@ -412,6 +423,7 @@ def main():
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-allreduce", action="store_true", help="N>1: all-reduce the whole gradient (no t-slab ownership)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the step instead of grid-first overlap")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

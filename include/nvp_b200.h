@@ -137,6 +137,15 @@ int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords
                      float* loss_sum, float* out_rgb, void* workspace, size_t workspace_bytes,
                      int mode, void* stream);
 
+/* Multi-GPU overlap hook (reference counterpart: none - the reference is single-GPU, training.py:74).
+ * Inside nvp_backward / nvp_fwd_loss_bwd the grid scatter-add runs before the weight-gradient kernel.  If an event was
+ * registered with this call (cudaEvent_t as void*, thread-local, consumed by the next backward call of this thread; NULL
+ * clears), it is recorded on the call's stream right after the scatter-add: the keyframe / sparse-grid gradients are
+ * then final, so the host can start their collective on another stream while the MLP weight gradients are still
+ * being computed; that kernel then leaves NVP_COMM_SMS (env, default 16) SMs free for the collective's CTAs
+ * (tensor-core mode; the fp32 mode records the event after its last kernel). */
+int nvp_record_grid_grads_event(void* cuda_event);
+
 /* Number of kernels the last call on this thread enqueued (for bench.py's gpu_launches). */
 int nvp_last_launch_count(void);
 

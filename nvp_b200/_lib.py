@@ -43,6 +43,7 @@ EXPORTS = (
     "nvp_version", "nvp_last_error", "nvp_level_table", "nvp_latent_dim", "nvp_workspace_bytes",
     "nvp_encode_latent", "nvp_forward", "nvp_backward", "nvp_fwd_loss_bwd", "nvp_last_launch_count",
     "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step", "nvp_sample_batch", "nvp_scatter_latent",
+    "nvp_record_grid_grads_event",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -72,6 +73,7 @@ def load() -> C.CDLL:
     lib.nvp_fwd_loss_bwd.argtypes = [D, P, vp, vp, vp, i64, i64, P, vp, vp, vp, C.c_size_t, i32, vp]
     lib.nvp_adamw_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, i32, vp]
     lib.nvp_sample_batch.argtypes = [vp, i32, i32, i32, vp, vp, i64, vp, vp, C.c_uint64, C.c_uint64, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.nvp_record_grid_grads_event.argtypes = [vp]
     lib.nvp_profile_enable.argtypes = [i32]
     lib.nvp_profile_read.argtypes = [i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.nvp_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]

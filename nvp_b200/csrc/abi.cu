@@ -10,6 +10,7 @@ namespace nvp {
 
 static thread_local std::string g_error;
 static thread_local int g_launches = 0;
+static thread_local cudaEvent_t g_grid_event = nullptr;
 
 struct Profiler {
   bool on = false;
@@ -38,6 +39,11 @@ void prof_stop(cudaStream_t st) {
 void set_error(const std::string& msg) { g_error = msg; }
 void count_launch(int n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
+cudaEvent_t take_grid_event() {
+  cudaEvent_t e = g_grid_event;
+  g_grid_event = nullptr;
+  return e;
+}
 
 int validate_desc(const nvp_desc* d) {
   NVP_CHECK(d != nullptr, "nvp_desc is NULL");
@@ -114,6 +120,11 @@ int nvp_version(void) { return 100; }
 const char* nvp_last_error(void) { return g_error.c_str(); }
 
 int nvp_last_launch_count(void) { return g_launches; }
+
+int nvp_record_grid_grads_event(void* cuda_event) {
+  g_grid_event = static_cast<cudaEvent_t>(cuda_event);
+  return 0;
+}
 
 int nvp_latent_dim(const nvp_desc* d) { return d ? latent_dim(d) : -1; }
 

@@ -16,6 +16,8 @@ constexpr int kHidden = 128;
 void set_error(const std::string& msg);
 void count_launch(int n = 1);
 void reset_launch_count();
+// Event registered with nvp_record_grid_grads_event for the current backward call (cleared by the read), or nullptr.
+cudaEvent_t take_grid_event();
 
 #define NVP_CHECK(cond, msg)                                   \
   do {                                                         \

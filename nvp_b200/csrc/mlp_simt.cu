@@ -421,6 +421,7 @@ int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, co
     if ((rc = linear_dgrad(w.dM, p->mod_w[0], Z, Z, 1, w.dZ, w.ldz, m, st))) return rc;
     if ((rc = launch_grid_scatter(d, tab, coords + 3 * s0, m, w.dZ, w.ldz, nullptr, 0, 1.0f, nullptr, g, st))) return rc;
   }
+  if (cudaEvent_t ev = take_grid_event()) NVP_CUDA(cudaEventRecord(ev, st));   // nvp_record_grid_grads_event
   return 0;
 }
 

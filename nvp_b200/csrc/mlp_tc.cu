@@ -1244,13 +1244,27 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
     NVP_LAUNCH_CHECK();
   }
 
-  // 6. weight gradients
+  // 6. scatter-add into the grids (dz is still multiplied by gs).  It runs before the weight-gradient kernel so that a
+  //    multi-GPU host can start the collective on the grid gradients (the bulk of the all-reduce) while wgrad computes.
+  if (w.binws) rc = launch_grid_scatter_binned(d, tab, coords, n, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, w.binws, st);
+  else rc = launch_grid_scatter(d, tab, coords, n, nullptr, 0, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, st);
+  if (rc) return rc;
+  // With an event registered the host is about to run a collective next to the weight-gradient kernel: that kernel is
+  // persistent with ~200 KB of shared memory per CTA, so a few SMs are left free for the collective's CTAs.
+  int comm_sms = 0;
+  if (cudaEvent_t ev = take_grid_event()) {
+    NVP_CUDA(cudaEventRecord(ev, st));
+    const char* v = getenv("NVP_COMM_SMS");
+    comm_sms = std::max(0, std::min(num_sms() / 2, v && *v ? atoi(v) : 16));
+  }
+
+  // 7. weight gradients
   {
     WgArgs wa{};
     wa.dpre = w.dpre; wa.stash = w.stash; wa.z16t = w.z16t; wa.gscale = w.gscale;
     for (int i = 0; i < 3; ++i) { wa.g_mod_w[i] = g->mod_w[i]; wa.g_mod_b[i] = g->mod_b[i]; wa.g_siren_w[i] = g->siren_w[i]; }
     wa.n_units = 2 * n_tiles; wa.KZ = m.KZ; wa.Z = m.Z; wa.ZP = m.ZP;
-    build_wgrad_plan(wa, num_sms());
+    build_wgrad_plan(wa, num_sms() - comm_sms);
     int max_hp = 0;
     for (int k = 0; k < wa.n_kinds; ++k) max_hp = std::max(max_hp, wa.kind[k].n_hp);
     const size_t smem = 2 * static_cast<size_t>(max_hp) * kHalfPanelBytes + 1024;
@@ -1261,9 +1275,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
     NVP_LAUNCH_CHECK();
   }
 
-  // 7. scatter-add into the grids (dz is still multiplied by gs)
-  if (w.binws) return launch_grid_scatter_binned(d, tab, coords, n, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, w.binws, st);
-  return launch_grid_scatter(d, tab, coords, n, nullptr, 0, w.dz16t, m.KZ, 1.0f, w.gscale + 1, g, st);
+  return 0;
 }
 
 }  // namespace nvp

@@ -113,8 +113,11 @@ def backward(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequence
 
 def fwd_loss_bwd(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequence[Optional[torch.Tensor]],
                  coords: torch.Tensor, tsteps: torch.Tensor, gt_u8: torch.Tensor, n_global: int,
-                 loss_sum: torch.Tensor, mode: int, out_rgb: Optional[torch.Tensor] = None) -> None:
-    """One fused step: loss_sum[0] += sum((rgb-gt)^2); grads += d(mean over 3*n_global)/d(params)."""
+                 loss_sum: torch.Tensor, mode: int, out_rgb: Optional[torch.Tensor] = None,
+                 grid_event: Optional[torch.cuda.Event] = None) -> None:
+    """One fused step: loss_sum[0] += sum((rgb-gt)^2); grads += d(mean over 3*n_global)/d(params).
+    grid_event (optional) is recorded on the current stream as soon as the grid gradients are final, before the MLP
+    weight gradients are computed (nvp_record_grid_grads_event): the multi-GPU host starts its collective there."""
     coords = _require_cuda("all_coords", coords, torch.float32)
     tsteps = _require_cuda("temporal_steps", tsteps, torch.float32)
     gt_u8 = _require_cuda("img", gt_u8, torch.uint8)
@@ -123,6 +126,10 @@ def fwd_loss_bwd(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequ
     with torch.cuda.device(coords.device):
         ws = WORKSPACE.get(coords.device, _lib.workspace_bytes(desc, n, mode, 1))
         pp, gg = pack_ptrs(params), pack_ptrs(grads)
+        if grid_event is not None:
+            if not grid_event.cuda_event:                    # torch creates the handle lazily
+                grid_event.record(torch.cuda.current_stream(coords.device))
+            _lib.check(_lib.load().nvp_record_grid_grads_event(grid_event.cuda_event), "nvp_record_grid_grads_event")
         rc = _lib.load().nvp_fwd_loss_bwd(C.byref(desc), C.byref(pp), coords.data_ptr(), tsteps.data_ptr(),
                                           gt_u8.data_ptr(), n, n_global, C.byref(gg), loss_sum.data_ptr(),
                                           _ptr(out_rgb), ws.data_ptr(), ws.numel(), mode, _stream_ptr(coords.device))

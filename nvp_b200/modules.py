@@ -91,7 +91,8 @@ class NVP(nn.Module):
         return functional.encode_latent(self.desc, self.hot_path_parameters(), all_coords.reshape(-1, 3))
 
     def fwd_loss_bwd(self, model_input, gt_u8: torch.Tensor, n_global: Optional[int] = None,
-                     loss_sum: Optional[torch.Tensor] = None, out_rgb: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     loss_sum: Optional[torch.Tensor] = None, out_rgb: Optional[torch.Tensor] = None,
+                     grid_event: Optional[torch.cuda.Event] = None) -> torch.Tensor:
         """Fused training step (training.py:47-52,74): accumulates d(image_mse)/d(params) into `.grad`
         (allocated zero-filled when None) and returns sum((rgb-gt)^2) as a 1-element device tensor
         (divide by 3*n_global for the loss).  gt_u8 is the raw uint8 `img` from the sampler."""
@@ -110,5 +111,6 @@ class NVP(nn.Module):
             grads.append(p.grad)
         if loss_sum is None:
             loss_sum = torch.zeros(1, dtype=torch.float32, device=coords.device)
-        functional.fwd_loss_bwd(self.desc, ps, grads, coords, tsteps, gt, n_global or n, loss_sum, self.mode, out_rgb)
+        functional.fwd_loss_bwd(self.desc, ps, grads, coords, tsteps, gt, n_global or n, loss_sum, self.mode, out_rgb,
+                                grid_event)
         return loss_sum

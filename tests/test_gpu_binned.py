@@ -112,3 +112,27 @@ def test_full_size_tables_binned_vs_direct():
     for name in ("keyframes_xy.params", "keyframes_yt.params", "keyframes_xt.params", "sparse_grid.embeddings"):
         assert rel_err(g_b[name], g_d[name]) <= 5e-3, name
         assert abs(float(g_b[name].double().sum()) - float(g_d[name].double().sum())) <= 1e-3 * float(g_d[name].double().abs().sum())
+
+
+def test_grid_grads_event_is_recorded_between_scatter_and_wgrad():
+    """nvp_record_grid_grads_event: the event handed to the fused step completes, results are unchanged, and a side stream
+    that waits on it sees the final grid gradients (what the multi-GPU host all-reduces under the wgrad kernel)."""
+    cfg = O.NVPConfig(t_resolution=6, x_resolution=20, y_resolution=24)
+    p = O.init_params(cfg, seed=3, grid_std=0.3)
+    n = 5000
+    coords, tsteps, gt = sampler_like_inputs(cfg, n, seed=12)
+    _, _, ref = run_step(cfg, p, coords, tsteps, gt)
+    m = make_model(cfg, p, mode="tc")
+    ev = torch.cuda.Event()
+    side = torch.cuda.Stream()
+    m.fwd_loss_bwd({"all_coords": coords.cuda()[None], "temporal_steps": tsteps.cuda()[None]}, gt.cuda(), grid_event=ev)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        snap = {k: v.grad.detach().clone() for k, v in m.named_parameters() if "keyframes" in k or "sparse_grid" in k}
+    torch.cuda.synchronize()
+    assert ev.query()
+    got = model_grads(m)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) <= 1e-4, k
+    for k, v in snap.items():
+        assert rel_err(v.cpu(), ref[k]) <= 1e-4, k
