@@ -97,14 +97,16 @@ def test_binned_agrees_with_direct_kernels_including_out_of_range_coordinates():
         assert rel_err(g_b[name], g_d[name]) <= 5e-3, name
 
 
-def test_full_size_tables_binned_vs_direct():
-    """Config S tables (16 levels up to 1443^2 cells, 600x300x300 voxels) at a reduced batch: binned and direct paths
-    agree, and the per-plane gradient mass equals the direct kernels' (nothing lost at window borders)."""
-    cfg = O.NVPConfig()
+@pytest.mark.parametrize("t_res,n", [(600, 1 << 17), (300, 1 << 17), (600, O.N_SAMPLES_PER_STEP)])
+def test_full_size_tables_binned_vs_direct(t_res, n):
+    """Config S tables (16 levels up to 1443^2 cells, T x 300 x 300 voxels; T = 600 Jockey / 300 ShakeNDry, BASELINE
+    configs[1..2]) at a reduced batch and at the full 1,245,184-sample batch: binned and direct paths agree, and the
+    per-plane gradient mass equals the direct kernels' (nothing lost at window borders)."""
+    cfg = O.NVPConfig(t_resolution=t_res)
     torch.manual_seed(0)
     m = make_model(cfg, None, mode="tc")
     p = {k: v.detach().cpu() for k, v in m.state_dict().items() if not k.startswith("wrapper.net.")}
-    n = 1 << 17
+    del m
     coords, tsteps, gt = sampler_like_inputs(cfg, n, seed=8)
     rgb_b, loss_b, g_b = run_step(cfg, p, coords, tsteps, gt, binned=True)
     rgb_d, loss_d, g_d = run_step(cfg, p, coords, tsteps, gt, binned=False)
