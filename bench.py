@@ -254,7 +254,7 @@ def run_ours(args):
     launches = [0]
 
     overlap = None
-    if world > 1 and not args.no_overlap:
+    if world > 1 and args.overlap:
         from nvp_b200.dist import GridFirstAllReduce, grid_grad_numel
         overlap = GridFirstAllReduce(reduce_view, min(grid_grad_numel(model, flat), reduce_view.numel()))
 
@@ -423,7 +423,9 @@ def main():
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-allreduce", action="store_true", help="N>1: all-reduce the whole gradient (no t-slab ownership)")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the step instead of grid-first overlap")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N>1: all-reduce the grid gradients under the wgrad kernel (dist.GridFirstAllReduce; validated on 2 GPUs "
+                         "only) instead of one all-reduce after the step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
