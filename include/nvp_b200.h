@@ -137,6 +137,14 @@ int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords
                      float* loss_sum, float* out_rgb, void* workspace, size_t workspace_bytes,
                      int mode, void* stream);
 
+/* Host-only query of the tile-binned grid plan (nvp_b200/csrc/grid_binned.cuh) the tensor-core mode uses for n samples;
+ * no reference counterpart (introspection for tests / tuning).  tiles_per_axis = TB; window_extent[l] = cells per axis of
+ * level l's shared-memory window (E_l = ceil(scale_l / TB) + 2, clipped to res_l + 1); window_base[l] = first region
+ * cell of level l, window_base[n_levels] = cells per region; chunk = samples per task; workspace = bytes of bucket state.
+ * Returns 0 with *tiles_per_axis = 0 when the configuration uses the direct kernels instead.  Any out pointer may be NULL. */
+int nvp_grid_bin_plan(const nvp_desc* d, int64_t n, int32_t* tiles_per_axis, int32_t* chunk, int32_t* window_extent,
+                      int32_t* window_base, size_t* workspace);
+
 /* Multi-GPU overlap hook (reference counterpart: none - the reference is single-GPU, training.py:74).
  * Inside nvp_backward / nvp_fwd_loss_bwd the grid scatter-add runs before the weight-gradient kernel.  If an event was
  * registered with this call (cudaEvent_t as void*, thread-local, consumed by the next backward call of this thread; NULL

@@ -43,7 +43,7 @@ EXPORTS = (
     "nvp_version", "nvp_last_error", "nvp_level_table", "nvp_latent_dim", "nvp_workspace_bytes",
     "nvp_encode_latent", "nvp_forward", "nvp_backward", "nvp_fwd_loss_bwd", "nvp_last_launch_count",
     "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step", "nvp_sample_batch", "nvp_scatter_latent",
-    "nvp_record_grid_grads_event",
+    "nvp_record_grid_grads_event", "nvp_grid_bin_plan",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     lib.nvp_adamw_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, i32, vp]
     lib.nvp_sample_batch.argtypes = [vp, i32, i32, i32, vp, vp, i64, vp, vp, C.c_uint64, C.c_uint64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.nvp_record_grid_grads_event.argtypes = [vp]
+    lib.nvp_grid_bin_plan.argtypes = [D, i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]
     lib.nvp_profile_enable.argtypes = [i32]
     lib.nvp_profile_read.argtypes = [i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.nvp_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -120,6 +122,18 @@ def workspace_bytes(desc: NvpDesc, n: int, mode: int, what: int) -> int:
     out = C.c_size_t(0)
     check(load().nvp_workspace_bytes(C.byref(desc), n, mode, what, C.byref(out)), "nvp_workspace_bytes")
     return int(out.value)
+
+
+def grid_bin_plan(desc: NvpDesc, n: int) -> dict:
+    """Host-only: the tile-binned grid plan used for n samples ({} when the direct kernels are used instead)."""
+    L = desc.n_levels
+    tb, chunk, ws = C.c_int32(0), C.c_int32(0), C.c_size_t(0)
+    ext, base = (C.c_int32 * L)(), (C.c_int32 * (L + 1))()
+    check(load().nvp_grid_bin_plan(C.byref(desc), n, C.byref(tb), C.byref(chunk), ext, base, C.byref(ws)), "nvp_grid_bin_plan")
+    if tb.value == 0:
+        return {}
+    return {"tiles_per_axis": tb.value, "chunk": chunk.value, "window_extent": list(ext), "window_base": list(base),
+            "workspace": int(ws.value)}
 
 
 PROFILE_KINDS = ("pack", "grid_gather", "mlp_forward", "mlp_backward", "mlp_wgrad", "grid_scatter", "fp32_mode", "misc", "grid_bin")

@@ -121,6 +121,17 @@ const char* nvp_last_error(void) { return g_error.c_str(); }
 
 int nvp_last_launch_count(void) { return g_launches; }
 
+int nvp_grid_bin_plan(const nvp_desc* d, int64_t n, int32_t* tiles_per_axis, int32_t* chunk, int32_t* window_extent,
+                      int32_t* window_base, size_t* workspace) {
+  LevelTab tab;
+  if (int rc = build_level_table(d, &tab, nullptr)) return rc;
+  int tb = 0, ch = 0;
+  grid_bin_plan_info(d, tab, n, &tb, &ch, window_extent, window_base, workspace);
+  if (tiles_per_axis) *tiles_per_axis = tb;
+  if (chunk) *chunk = ch;
+  return 0;
+}
+
 int nvp_record_grid_grads_event(void* cuda_event) {
   g_grid_event = static_cast<cudaEvent_t>(cuda_event);
   return 0;

@@ -86,6 +86,9 @@ int launch_grid_scatter(const nvp_desc* d, const LevelTab& tab, const float* coo
 // of the unit square they fall into (launch_grid_bin, once per call) and the gather / scatter-add work on private
 // shared-memory windows.  grid_bin_workspace_bytes == 0 means "not available for this configuration".
 size_t grid_bin_workspace_bytes(const nvp_desc* d, const LevelTab& tab, int64_t n);
+// Host-side description of the plan (nvp_grid_bin_plan); tb = 0: not binned.  extent/base may be nullptr.
+void grid_bin_plan_info(const nvp_desc* d, const LevelTab& tab, int64_t n, int* tb, int* chunk, int32_t* extent, int32_t* base,
+                        size_t* workspace);
 int launch_grid_bin(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, int kz, void* binws,
                     cudaStream_t st);
 int launch_grid_gather_binned(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,

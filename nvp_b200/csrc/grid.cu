@@ -984,6 +984,20 @@ size_t grid_bin_workspace_bytes(const nvp_desc* d, const LevelTab& tab, int64_t 
   return plan_bins(d, tab, n, &pl) ? pl.total + 256 : 0;
 }
 
+void grid_bin_plan_info(const nvp_desc* d, const LevelTab& tab, int64_t n, int* tb, int* chunk, int32_t* extent, int32_t* base,
+                        size_t* workspace) {
+  BinPlan pl;
+  const bool ok = plan_bins(d, tab, n, &pl);
+  if (tb) *tb = ok ? pl.bt.tb : 0;
+  if (chunk) *chunk = ok ? pl.bt.chunk : 0;
+  if (workspace) *workspace = ok ? pl.total + 256 : 0;
+  for (int l = 0; ok && l < tab.n_levels; ++l) {
+    if (extent) extent[l] = pl.bt.E[l];
+    if (base) base[l] = pl.bt.base[l];
+  }
+  if (ok && base) base[tab.n_levels] = pl.bt.base[tab.n_levels];
+}
+
 int launch_grid_bin(const nvp_desc* d, const LevelTab& tab, const float* coords, int64_t n, int kz, void* binws,
                     cudaStream_t st) {
   BinPlan pl;

@@ -41,7 +41,7 @@ for r in rows[2:]:
     b = float(r[ri]) * unit[rows[1][ri]] + float(r[wi]) * unit[rows[1][wi]]
     traffic[kind] = traffic.get(kind, 0.0) + b
 with open(os.path.join(root, f"{tag}_traffic_{config}.json"), "w") as f:
-    json.dump({"source": f"ncu --set full --clock-control none capture of `python prof_step.py 2` (one step's kernels), {tag}; "
+    json.dump({"source": f"ncu --set full --clock-control none capture of `python scripts/prof_step.py 2` (one step's kernels), {tag}; "
                          "dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of each kind",
                "dram_bytes_per_step": traffic}, f, indent=1)
 print(json.dumps(traffic, indent=1))
