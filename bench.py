@@ -222,7 +222,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a collective that does not complete within 3 minutes aborts the job (NCCL watchdog) instead of spinning on the GPUs
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
     cfg_json = load_config(args.config)
