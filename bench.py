@@ -199,10 +199,11 @@ def bench_config(args, mode):
     return {"workload": f"synthetic 1920x1080x600 (UVG Jockey stand-in), config_nvp_{args.config}, "
                         f"{N_SAMPLES} sampled coordinates per step per GPU",
             "nvp_config": f"config_nvp_{args.config}", "samples_per_step_per_gpu": N_SAMPLES, "mode": mode,
-            "step": "grad-buffer zero + gather + fused MLP fwd + L2 loss + fused bwd + wgrad + grid scatter"
+            "step": "grad-buffer zero + sample bucketing + grid gather + fused MLP fwd + L2 loss + fused bwd + grid scatter-add + wgrad"
                     + ((" + NCCL all-reduce of the whole flat gradient buffer" if args.full_allreduce else
                         " + NCCL all-reduce of keyframe+MLP gradients (sparse 3-D grid owned per rank by t-slab, samples "
-                        "stratified by slab)") if args.gpus > 1 else ""),
+                        "stratified by slab)") + (", grid piece overlapped with wgrad" if getattr(args, "overlap", False) else "")
+                       if args.gpus > 1 else ""),
             "l2": "working set >> L2 (543 MB params + 543 MB grads + 4.6 GB activation tiles per step); 8 rotating input batches",
             "parallelism": f"dp{args.gpus}"}
 
