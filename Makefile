@@ -2,6 +2,10 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+# make TIMELINE=1: compile the in-kernel clock64 timeline of the fused forward kernel in (development only)
+ifdef TIMELINE
+NVCCFLAGS += -DNVP_TIMELINE
+endif
 SRC       := $(wildcard nvp_b200/csrc/*.cu)
 HDR       := $(wildcard nvp_b200/csrc/*.cuh) include/nvp_b200.h
 OBJDIR    := build/obj

@@ -145,6 +145,11 @@ int nvp_fwd_loss_bwd(const nvp_desc* d, const nvp_params* p, const float* coords
 int nvp_grid_bin_plan(const nvp_desc* d, int64_t n, int32_t* tiles_per_axis, int32_t* chunk, int32_t* window_extent,
                       int32_t* window_base, size_t* workspace);
 
+/* Development aid, no reference counterpart: clock64 stamps of the fused forward kernel's phases (CTA 0, 4th tile), only in
+ * libraries built with `make TIMELINE=1`; otherwise returns nonzero.  out has room for n (<= 128) host uint64 slots; call
+ * after synchronising the stream. */
+int nvp_debug_timeline_read(uint64_t* out, int32_t n);
+
 /* Multi-GPU overlap hook (reference counterpart: none - the reference is single-GPU, training.py:74).
  * Inside nvp_backward / nvp_fwd_loss_bwd the grid scatter-add runs before the weight-gradient kernel.  If an event was
  * registered with this call (cudaEvent_t as void*, thread-local, consumed by the next backward call of this thread; NULL

@@ -43,7 +43,7 @@ EXPORTS = (
     "nvp_version", "nvp_last_error", "nvp_level_table", "nvp_latent_dim", "nvp_workspace_bytes",
     "nvp_encode_latent", "nvp_forward", "nvp_backward", "nvp_fwd_loss_bwd", "nvp_last_launch_count",
     "nvp_selftest_umma", "nvp_profile_enable", "nvp_profile_read", "nvp_adamw_step", "nvp_sample_batch", "nvp_scatter_latent",
-    "nvp_record_grid_grads_event", "nvp_grid_bin_plan",
+    "nvp_record_grid_grads_event", "nvp_grid_bin_plan", "nvp_debug_timeline_read",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.nvp_adamw_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, i32, vp]
     lib.nvp_sample_batch.argtypes = [vp, i32, i32, i32, vp, vp, i64, vp, vp, C.c_uint64, C.c_uint64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.nvp_record_grid_grads_event.argtypes = [vp]
+    lib.nvp_debug_timeline_read.argtypes = [C.POINTER(C.c_uint64), C.c_int32]
     lib.nvp_grid_bin_plan.argtypes = [D, i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]
     lib.nvp_profile_enable.argtypes = [i32]

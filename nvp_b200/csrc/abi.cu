@@ -132,6 +132,11 @@ int nvp_grid_bin_plan(const nvp_desc* d, int64_t n, int32_t* tiles_per_axis, int
   return 0;
 }
 
+int nvp_debug_timeline_read(uint64_t* out, int32_t n) {
+  NVP_CHECK(out != nullptr && n > 0, "out is NULL / n <= 0");
+  return tc_timeline_read(reinterpret_cast<unsigned long long*>(out), n);
+}
+
 int nvp_record_grid_grads_event(void* cuda_event) {
   g_grid_event = static_cast<cudaEvent_t>(cuda_event);
   return 0;

@@ -110,6 +110,7 @@ int simt_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, co
 
 // ---- mlp_tc.cu ----------------------------------------------------------------------------
 size_t tc_workspace_bytes(const nvp_desc* d, int64_t n, int what);
+int tc_timeline_read(unsigned long long* out, int n);   // NVP_TIMELINE builds only
 int tc_forward(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, const float* coords,
                const float* tsteps, int64_t n, float* out_rgb, void* ws, size_t ws_bytes, cudaStream_t st,
                bool temporal_interp = false);

@@ -28,6 +28,17 @@ constexpr int H = kHidden;          // 128
 constexpr int kTile = 128;          // samples per tile (UMMA M)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
+
+// Optional in-kernel timeline (make TIMELINE=1): clock64 stamps of CTA 0 in its 4th tile, read back with
+// nvp_debug_timeline_read / scripts/mlp_timeline.py.  Forward: slot = 16*step + 8*panel + k for the epilogue issuer
+// (k: 0 accumulators ready, 1 TMEM loaded, 2 tile stored to smem, 3 after the phase barrier), 64 + 8*step + k for the
+// MMA thread (k: 0 step start, 1..2 panel q of h/a available, 3 all MMAs issued).  Compiled out by default.
+#ifdef NVP_TIMELINE
+__device__ unsigned long long g_timeline[128];
+#define NVP_TL(cond, slot) do { if (blockIdx.x == 0 && (cond)) g_timeline[(slot)] = clock64(); } while (0)
+#else
+#define NVP_TL(cond, slot) do {} while (0)
+#endif
 constexpr int kMaxPack = 72;
 
 // ------------------------------------------------------------------------------------------
@@ -303,6 +314,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
         const uint32_t par = it & 1;
         mbar_wait(zfull, par);
         for (int step = 0; step < 3; ++step) {
+          NVP_TL(it == 3, 64 + 8 * step);
           const uint32_t b = (3 * it + step) & 1;
           const uint32_t acc_m = tmem + 128 * b, acc_s = tmem + 256 + 128 * b;
           // accumulator set b was last read by the epilogue two steps ago; for step 1 that is the previous
@@ -315,12 +327,14 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
           if (step > 0) {
             for (int q = 0; q < 2; ++q) {
               mbar_wait(&panel_done[(step - 1) * 2 + q], par);
+              NVP_TL(it == 3, 64 + 8 * step + 1 + q);
               tcgen05_fence_after();
               gemm_panel(smem_u32(hbuf + q * kPanelBytes), acc_m, first_m);
               gemm_panel(smem_u32(abuf + q * kPanelBytes), acc_s, first_s);
             }
           }
           umma_commit(acc_full);
+          NVP_TL(it == 3, 64 + 8 * step + 3);
         }
       }
     }
@@ -343,6 +357,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
         const uint32_t acc_m = tmem + 128 * b, acc_s = tmem + 256 + 128 * b;
         mbar_wait(acc_full, n_acc & 1); ++n_acc;
         tcgen05_fence_after();
+        NVP_TL(issuer && it == 3, 16 * step);
 #pragma unroll 1
         for (int p = 0; p < 2; ++p) {
           const int pc = sub * CW;           // column inside panel p
@@ -352,6 +367,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
           }
+          NVP_TL(issuer && it == 3 && p == 1, 16 * step + 8);
           uint32_t vm[CW];
           tmem_ldn<CW>(acc_m + lane_base + col, vm);
           float hv[CW], av[CW];
@@ -382,6 +398,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
               store_rown<CW>(st_base + (static_cast<size_t>(step == 1 ? SL_C1 : SL_C2) * 2 + p) * kPanelBytes, r, pc, cv);
             }
           }
+          NVP_TL(issuer && it == 3, 16 * step + 8 * p + 1);   // TMEM loaded, activation math done
           if (step < 2 || TRAIN) store_rown<CW>(hbuf + p * kPanelBytes, r, pc, hv);
           if (step < 2) {
             store_rown<CW>(abuf + p * kPanelBytes, r, pc, av);
@@ -394,9 +411,11 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) mlp_forward_kernel(const FwdA
             }
             if (p == 1 && sub > 0) { float* x = s_rgbx + ((sub - 1) * H + r) * 3; x[0] = rgb0; x[1] = rgb1; x[2] = rgb2; }
           }
+          NVP_TL(issuer && it == 3, 16 * step + 8 * p + 2);
           fence_proxy_async_smem();   // st.shared operand / staging tiles -> visible to UMMA and TMA (async proxy)
           tcgen05_fence_before();
           asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");
+          NVP_TL(issuer && it == 3, 16 * step + 8 * p + 3);
           if (issuer) {
             mbar_arrive(&panel_done[step * 2 + p]);   // first: the MMA warp is on the critical path, the stash stores are not
             if (TRAIN) {
@@ -1160,6 +1179,16 @@ int launch_forward(const nvp_desc* d, const nvp_params* p, const TcWorkspace& w,
 }
 
 }  // namespace
+
+int tc_timeline_read(unsigned long long* out, int n) {
+#ifdef NVP_TIMELINE
+  NVP_CUDA(cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * std::min(n, 128)));
+  return 0;
+#else
+  (void)out; (void)n;
+  NVP_CHECK(false, "library built without the in-kernel timeline (make TIMELINE=1)");
+#endif
+}
 
 size_t tc_workspace_bytes(const nvp_desc* d, int64_t n, int what) { return carve_tc(d, std::max<int64_t>(n, 1), what, nullptr).total; }
 
