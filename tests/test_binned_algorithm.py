@@ -1,0 +1,94 @@
+"""CPU test of the tile-binned grid ALGORITHM (what csrc/grid_binned.cuh computes), restated in numpy from the plan the
+library reports (nvp_grid_bin_plan) and compared with the oracle's DenseGrid forward / backward.
+
+It pins the index logic independently of the CUDA code: bucketing by tile, the per-level window with its aliased
+"virtual" cells (res, j) / (i, res) (unclamped flat index, then modulo the level size - SURVEY A.2), the direct-access
+branch for samples outside their tile's window (coordinates outside [0,1]) and the flush of a window onto the table.
+The GPU tests check that the kernels implement exactly this (tests/test_gpu_binned.py)."""
+import numpy as np
+import pytest
+import torch
+
+from nvp_b200 import _lib
+from oracle import nvp_oracle as O
+
+
+def wrap(flat, cells):
+    return np.mod(flat, cells)
+
+
+def emulate(u, table, F, plan, params=None, dz=None):
+    """One keyframe plane.  Either params [cells*F] -> gather output [n, L*F], or dz [n, L*F] -> gradient table [cells*F]
+    (one direction per call: the window holds table values in the gather and partial sums in the scatter-add)."""
+    assert (params is None) != (dz is None)
+    tb, ext = plan["tiles_per_axis"], plan["window_extent"]
+    n, L = u.shape[0], table.n_levels
+    out = np.zeros((n, L * F), np.float64) if params is not None else None
+    grad = np.zeros(int(table.offsets[-1]) * F, np.float64) if dz is not None else None
+    b = np.clip((u * np.float32(tb)).astype(np.int32), 0, tb - 1)        # bin_tile_axis (NaN-free inputs)
+    bucket = b[:, 1] * tb + b[:, 0]
+    for tile in np.unique(bucket):
+        sel = np.nonzero(bucket == tile)[0]
+        ub = np.array([tile % tb, tile // tb], np.float32) / np.float32(tb)
+        for l in range(L):
+            s, res, E, off = table.scales[l], int(table.res[l]), ext[l], int(table.offsets[l])
+            cells = res * res
+            lo = np.floor(O._fmaf(np.full(2, s, np.float32), ub, 0.5)).astype(np.int64)
+            amax = np.minimum(E - 2, res - 1 - lo)
+            # window <-> table map, including the virtual cells; cells beyond (res, res) do not exist
+            a_idx, b_idx = np.meshgrid(np.arange(E), np.arange(E), indexing="xy")
+            g0, g1 = lo[0] + a_idx, lo[1] + b_idx
+            ok = (g0 <= res) & (g1 <= res)
+            glob = off + wrap(g0 + g1 * res, cells)
+            win = np.zeros((E, E, F), np.float64)                          # [b, a, f]
+            if params is not None:
+                tabv = params.reshape(-1, F)
+                win[ok] = tabv[glob[ok]]
+            pos = O._fmaf(np.full((len(sel), 2), s, np.float32), u[sel], 0.5)
+            fl = np.floor(pos)
+            w = (pos - fl).astype(np.float32)
+            i = fl.astype(np.int64)
+            aa, bb = i[:, 0] - lo[0], i[:, 1] - lo[1]
+            inside = (aa >= 0) & (aa <= amax[0]) & (bb >= 0) & (bb <= amax[1])
+            for k, smp in enumerate(sel):
+                for c1 in (0, 1):
+                    for c0 in (0, 1):
+                        wt = float((w[k, 0] if c0 else np.float32(1) - w[k, 0]) * (w[k, 1] if c1 else np.float32(1) - w[k, 1]))
+                        if inside[k]:
+                            cell = (bb[k] + c1, aa[k] + c0)
+                            if params is not None:
+                                out[smp, l * F:(l + 1) * F] += wt * win[cell]
+                            if dz is not None:
+                                win[cell] += wt * dz[smp, l * F:(l + 1) * F]
+                        else:                                               # direct global access, modulo the level
+                            gi = off + int(wrap((i[k, 0] + c0) + (i[k, 1] + c1) * res, cells))
+                            if params is not None:
+                                out[smp, l * F:(l + 1) * F] += wt * params.reshape(-1, F)[gi]
+                            if dz is not None:
+                                grad.reshape(-1, F)[gi] += wt * dz[smp, l * F:(l + 1) * F]
+            if dz is not None:                                              # flush: one add per window cell
+                np.add.at(grad.reshape(-1, F), glob[ok], win[ok])
+    return out, grad
+
+
+@pytest.mark.parametrize("F", [2, 4])
+def test_binned_algorithm_equals_the_oracle_including_edges_and_out_of_range(F):
+    L = 16
+    d = _lib.NvpDesc(F, L, 16, 1.35, F, 6, 20, 24, 128, 3, 30.0)
+    plan = _lib.grid_bin_plan(d, 4096)
+    assert plan
+    table = O.level_table(L, 16, 1.35)
+    rng = np.random.default_rng(F)
+    vals = np.array([0.0, 1.0, 0.5, 63.0 / 64, 1.0 / 1079, 1078.0 / 1079, 127.0 / 128], np.float32)
+    edge = np.stack(np.meshgrid(vals, vals), -1).reshape(-1, 2)
+    u = np.concatenate([rng.random((260, 2)).astype(np.float32), edge,
+                        (rng.random((40, 2)) * 1.6 - 0.3).astype(np.float32)])          # some outside [0,1]
+    n = u.shape[0]
+    params = torch.from_numpy(rng.standard_normal(int(table.offsets[-1]) * F)).double().requires_grad_(True)
+    dz = rng.standard_normal((n, L * F))
+    ref = O.dense_grid_forward(params, torch.from_numpy(u), F, table)
+    (ref * torch.from_numpy(dz)).sum().backward()
+    out, _ = emulate(u, table, F, plan, params=params.detach().numpy())      # gather: windows loaded from the table
+    _, grad = emulate(u, table, F, plan, dz=dz)                               # scatter-add: windows start at zero
+    assert np.abs(out - ref.detach().numpy()).max() <= 1e-9
+    assert np.abs(grad - params.grad.numpy()).max() <= 1e-9
