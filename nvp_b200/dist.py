@@ -72,16 +72,20 @@ class GridFirstAllReduce:
         self.grid = reduce_view[:grid_numel]
         self.rest = reduce_view[grid_numel:]
         self.group = group
-        self.event = torch.cuda.Event()
-        self.side = torch.cuda.Stream(reduce_view.device)
+        self.cuda = reduce_view.is_cuda          # CPU tensors (gloo tests): same two pieces, no streams / events
+        self.event = torch.cuda.Event() if self.cuda else None
+        self.side = torch.cuda.Stream(reduce_view.device) if self.cuda else None
 
     def run(self) -> None:
         # Both pieces are issued with async_op=True so that both run on the process group's own NCCL stream, in this
         # order on every rank.  (A synchronous collective may be enqueued on the *calling* stream instead; mixed with an
         # asynchronous one that lets two kernels of one communicator run concurrently, which NCCL does not allow - the
         # first version of this class did that and hung at 8 GPUs once the grid piece outlasted the wgrad kernel.)
-        self.side.wait_event(self.event)
-        with torch.cuda.stream(self.side):
+        if self.cuda:
+            self.side.wait_event(self.event)
+            with torch.cuda.stream(self.side):
+                w_grid = dist.all_reduce(self.grid, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
             w_grid = dist.all_reduce(self.grid, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         w_rest = dist.all_reduce(self.rest, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if self.rest.numel() else None
         w_grid.wait()

@@ -107,3 +107,40 @@ def test_two_rank_gloo_shards_sum_to_the_global_gradient():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _grid_first_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nvp_b200.dist import GridFirstAllReduce, grid_grad_numel
+    import types
+    # a stand-in with the attribute names grid_grad_numel looks at: three keyframe planes + the sparse grid first,
+    # then two MLP tensors, all with gradients in one flat buffer (attach_flat_grads order = parameters() order)
+    m = torch.nn.Module()
+    for name, n in (("keyframes_xy", 70), ("keyframes_yt", 70), ("keyframes_xt", 70)):
+        enc = torch.nn.Module(); enc.params = torch.nn.Parameter(torch.zeros(n)); setattr(m, name, enc)
+    m.sparse_grid = torch.nn.Module(); m.sparse_grid.embeddings = torch.nn.Parameter(torch.zeros(3, 4, 5, 2))
+    m.net = torch.nn.Linear(5, 3)
+    flat = attach_flat_grads(m)
+    k = grid_grad_numel(m, flat)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat.copy_(torch.randn(flat.numel(), generator=g))
+    expect = sum(torch.randn(flat.numel(), generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    ar = GridFirstAllReduce(flat, k)
+    ar.run()
+    ok = k == m.net.weight.grad.data_ptr() // 4 - flat.data_ptr() // 4 and k >= 3 * 70 + 120
+    ok = ok and torch.allclose(flat, expect, atol=1e-6)
+    # degenerate split: everything in the grid piece
+    flat2 = torch.full((64,), float(rank + 1))
+    GridFirstAllReduce(flat2, 64).run()
+    ok = ok and bool((flat2 == sum(range(1, world + 1))).all())
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_grid_first_all_reduce_equals_one_all_reduce():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_grid_first_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
