@@ -5,19 +5,22 @@
 // (measured 1.29 cycles per lane-level red.global on this part: 240 M of them = 1.1 ms of a 4.7 ms step).
 //
 // Here the samples of a call are first bucketed, per keyframe plane, by the TB x TB tile of the unit square their
-// plane coordinates (u0, u1) fall into (grid_bin_* kernels: histogram, scan + task list, fill).  All samples of one
-// tile touch, at level l, only the cells of a small window: E_l = ceil(scale_l / TB) + 2 cells per axis
-// (13 KB for all 16 levels of config S at TB = 64).  One WARP owns one task (a tile, or a chunk of a crowded tile):
-//   gather : the window is copied from the plane table into the warp's private shared-memory region with coalesced
-//            row reads; each sample is then interpolated from shared memory by the 32 lanes = 16 levels x 2 cell
-//            rows (two adjacent corners per lane) and the two row partial sums meet in one warp shuffle;
-//   scatter: the region starts at zero, every sample does a plain (non-atomic) read-modify-write of its corners -
-//            lanes of one sample never collide (different levels / different rows), consecutive samples are ordered
-//            by __syncwarp - and the region is flushed once per task with one vector reduction per touched cell:
-//            ~2.6 global reductions per (sample, plane) instead of 64.
+// plane coordinates (u0, u1) fall into (grid_bin_* kernels: histogram, scan + task list, fill; TB = 128 by default).
+// All samples of one tile touch, at level l, only the cells of a small window: E_l = ceil(scale_l / TB) + 2 cells per
+// axis (619 cells = 5 KB for all 16 levels of config S).  One WARP owns one task (a tile, or a chunk of a crowded tile)
+// and a private window region in shared memory:
+//   gather : the window is copied from the plane table with cp.async (rows coalesced, all cells in flight together);
+//            then lane = sample: every lane walks the levels, reads its 4 corners from the window and writes its slice
+//            of the latent row as whole 16-byte chunks - same corner order and fma chain as the direct kernel;
+//   scatter: lane = (level, cell row): the region starts at zero, the warp takes one sample per step and every lane does
+//            a plain (non-atomic) read-modify-write of two adjacent corners - lanes of one sample never collide
+//            (different levels / rows), consecutive samples are ordered by __syncwarp - and the region is flushed once
+//            per task with one vector reduction per non-zero cell: ~8 global reductions per (sample, plane), not 64.
 // Cell addressing keeps the reference's edge behaviour (flat index without clamping, then modulo the level size,
-// SURVEY.md A.2): the window stores the "virtual" cell (res, j) separately and maps it to its alias on load / flush.
-// Samples whose cells fall outside the window (coordinates outside [0,1]) take the direct global path.
+// SURVEY.md A.2): the window stores the "virtual" cells (res, j) / (i, res) and maps them to their aliases on load /
+// flush.  Samples whose cells fall outside the window (coordinates outside [0,1]) take the direct global path.
+// The 3x3 voxel neighbourhood of the 3-D grid (DRAM-latency-bound) runs as a few extra warps of the same CTAs.
+// tests/test_binned_algorithm.py restates this algorithm in numpy and checks it against the oracle on CPU.
 #pragma once
 // (no namespace of its own: grid.cu includes this file inside nvp::<anonymous>, after the helpers it uses)
 
@@ -36,7 +39,7 @@ struct BinArgs {
   int32_t n;
   // bucket state (caller workspace)
   int32_t* cnt;            // [3 * nt]     samples per (plane, tile)
-  int32_t* offs;           // [3 * nt + 1] exclusive prefix of cnt (positions into perm)
+  int32_t* offs;           // [3 * nt + 1] exclusive prefix of cnt (positions into recs)
   int32_t* cursor;         // [3 * nt]     fill cursors
   int2* tasks;             // [max_tasks]  (bucket, first position)
   int32_t* n_tasks;        // [1]
