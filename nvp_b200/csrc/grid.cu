@@ -5,7 +5,11 @@
 //   sparse 3-D grid  = nearest voxel + 3x3 (x,y) neighbourhood   (reference: sparsegrid.py:43-72)
 //   latent column order: xy | yt | xt | sparse                   (reference: modules.py:69,78)
 //
-// Thread mapping: one thread per (sample, level); the L threads of one sample are adjacent lanes, so
+// This file holds the DIRECT kernels (one scattered access per corner; used by the fp32 mode, the standalone encode /
+// scatter entry points and as the fallback of the tensor-core mode) and the host side of the tile-binned kernels of
+// grid_binned.cuh, which the tensor-core mode uses for both reference configurations.
+//
+// Thread mapping of the direct kernels: one thread per (sample, level); the L threads of one sample are adjacent lanes, so
 // every plane's L*F output floats are written as one contiguous run and the three coordinate
 // loads are warp-broadcasts.  Threads with level index < 9 also fetch one voxel of the 3x3
 // neighbourhood.  All table reads go through the read-only path as F-wide vectors; the backward
