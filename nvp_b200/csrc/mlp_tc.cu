@@ -885,6 +885,7 @@ struct WgArgs {
   float* g_mod_b[3];
   float* g_siren_w[3];
   int n_units;   // half tiles
+  int stash_slots;   // stash tiles per 128 samples (SL_COUNT, or FS_COUNT behind the fused kernel; slots 0-3 are h0 a0 h1 a1)
   int KZ, Z, ZP;
   int n_kinds;
   WgKind kind[3];
@@ -925,7 +926,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgArgs a
         const int tile = u >> 1;
         const uint32_t hoff = static_cast<uint32_t>(u & 1) * kHalfPanelBytes;  // rows 0-63 or 64-127 of each panel
         const uint8_t* dp = a.dpre + static_cast<size_t>(tile) * DP_COUNT * 2 * kPanelBytes;
-        const uint8_t* sb = a.stash + static_cast<size_t>(tile) * SL_COUNT * 2 * kPanelBytes;
+        const uint8_t* sb = a.stash + static_cast<size_t>(tile) * a.stash_slots * 2 * kPanelBytes;
         const uint8_t* zt = a.z16t + static_cast<size_t>(tile) * a.KZ * kPanelBytes;
         for (int o = 0; o < K.n_ops; ++o) {
           const int src = K.op_src[o];
@@ -1082,7 +1083,10 @@ int pack_backward_panels(const nvp_desc* d, const nvp_params* p, PackArgs& a, ui
   return 0;
 }
 
+#include "mlp_fused.cuh"
+
 struct TcWorkspace {
+  uint8_t* wpk_fused;
   uint8_t* wpk_fwd;
   uint8_t* wpk_bwd;
   uint8_t* z16t;
@@ -1106,6 +1110,7 @@ TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
   TcWorkspace w{};
   w.wpk_fwd = take(m.fwd_bytes);
   w.wpk_bwd = take(static_cast<size_t>(8) * kPanelBytes + static_cast<size_t>(6) * m.ZP * 128);
+  w.wpk_fused = take(static_cast<size_t>(kFPanelsPerTile) * kPanelBytes);
   w.z16t = take(static_cast<size_t>(tiles) * m.KZ * kPanelBytes);
   w.rgb = reinterpret_cast<float*>(take(static_cast<size_t>(tiles) * kTile * 3 * sizeof(float)));
   {
@@ -1236,36 +1241,64 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
     NVP_LAUNCH_CHECK();
   }
 
-  // 2. weights -> fp16 panels (forward and backward streams in one launch)
+  // The fused forward+backward kernel covers latents of up to 127 columns (two 64-wide panels: config S); wider ones
+  // (config L) take the three-kernel path.  NVP_MLP_FUSED=0 forces the latter (A/B measurements).
+  static const bool fused_enabled = [] { const char* v = getenv("NVP_MLP_FUSED"); return !(v && atoi(v) == 0); }();
+  const bool fused = fused_enabled && m.KZ == 2;
+  float* rgb = out_rgb ? out_rgb : w.rgb;
   BwdArgs b{};
-  if ((rc = pack_forward_weights(d, p, w.wpk_fwd, &b, st, w.wpk_bwd))) return rc;
 
-  // 3. positional features, 4. fused forward (keeps the activation stash)
+  // 2. weights -> fp16 panels
+  if (fused) { if ((rc = pack_fused_weights(d, p, w.wpk_fused, st))) return rc; }
+  else if ((rc = pack_forward_weights(d, p, w.wpk_fwd, &b, st, w.wpk_bwd))) return rc;
+
+  // 3. positional features.  Rows past n of the last tile are never written by the gather: clear them so that the
+  //    dense layers see finite values there (their gradients are zero: dL/drgb = 0 for those rows).
+  if (n % kTile != 0)
+    NVP_CUDA(cudaMemsetAsync(w.z16t + static_cast<size_t>(n_tiles - 1) * m.KZ * kPanelBytes, 0, static_cast<size_t>(m.KZ) * kPanelBytes, st));
   if (w.binws) {
     if ((rc = launch_grid_bin(d, tab, coords, n, m.KZ, w.binws, st))) return rc;
     if ((rc = launch_grid_gather_binned(d, tab, p, coords, n, w.z16t, m.KZ, w.binws, st))) return rc;
   } else if ((rc = launch_grid_gather(d, tab, p, coords, n, nullptr, 0, w.z16t, m.KZ, st))) {
     return rc;
   }
-  float* rgb = out_rgb ? out_rgb : w.rgb;
-  if ((rc = launch_forward(d, p, w, tsteps, n, rgb, true, st))) return rc;
 
-  // 5. fused backward
-  b.wpk = w.wpk_bwd; b.stash = w.stash; b.tau = tsteps; b.rgb = rgb; b.gt = gt_u8; b.dout = dout; b.gscale = w.gscale;
-  b.siren_w0 = p->siren_w[0]; b.siren_b0 = p->siren_b[0]; b.last_w = p->last_w; b.w0 = d->w0_first;
-  b.dpre = w.dpre; b.dz16t = w.dz16t; b.loss_sum = loss_sum;
-  b.g_last_w = g->last_w; b.g_last_b = g->last_b; b.g_siren_b1 = g->siren_b[1]; b.g_siren_b2 = g->siren_b[2];
-  b.g_siren_w0 = g->siren_w[0]; b.g_siren_b0 = g->siren_b[0];
-  b.n = n; b.n_tiles = n_tiles; b.ZP = m.ZP; b.NZ = NZ;
-  b.stage_bytes = static_cast<uint32_t>(m.ZP) * 128u;
-  b.nstage = 0;
-  for (b.stage_dz = 1; b.stage_dz >= 0 && b.nstage == 0; --b.stage_dz) {
-    for (int ns = 12; ns >= 3; --ns)
-      if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes, m.ZP, b.stage_dz).total) <= kSmemBudget) { b.nstage = ns; break; }
-    if (b.nstage) break;
-  }
-  NVP_CHECK(b.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core backward");
-  {
+  if (fused) {
+    // 4+5. fused forward + loss + backward
+    FusedArgs f{};
+    f.wpk = w.wpk_fused; f.z16t = w.z16t; f.tau = tsteps;
+    for (int i = 0; i < 3; ++i) { f.mod_b[i] = p->mod_b[i]; f.siren_b[i] = p->siren_b[i]; }
+    f.siren_w0 = p->siren_w[0]; f.last_w = p->last_w; f.last_b = p->last_b; f.w0 = d->w0_first;
+    f.gt = gt_u8; f.dout = dout; f.gscale = w.gscale; f.rgb_out = out_rgb;
+    f.stash = w.stash; f.dpre = w.dpre; f.dz16t = w.dz16t; f.loss_sum = loss_sum;
+    f.g_last_w = g->last_w; f.g_last_b = g->last_b; f.g_siren_b1 = g->siren_b[1]; f.g_siren_b2 = g->siren_b[2];
+    f.g_siren_w0 = g->siren_w[0]; f.g_siren_b0 = g->siren_b[0];
+    f.n = n; f.n_tiles = n_tiles;
+    const size_t smem = fused_smem_layout().total + 1024;
+    static_assert(fused_smem_layout().total + 1024 <= 227 * 1024, "fused kernel: shared-memory plan exceeds 227 KiB");
+    NVP_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ScopedKernelTimer timer(K_MLP_BWD, st);
+    mlp_fused_kernel<<<std::min(n_tiles, num_sms()), kFThreads, smem, st>>>(f);
+    NVP_LAUNCH_CHECK();
+  } else {
+    // 4. fused forward (keeps the activation stash)
+    if ((rc = launch_forward(d, p, w, tsteps, n, rgb, true, st))) return rc;
+
+    // 5. fused backward
+    b.wpk = w.wpk_bwd; b.stash = w.stash; b.tau = tsteps; b.rgb = rgb; b.gt = gt_u8; b.dout = dout; b.gscale = w.gscale;
+    b.siren_w0 = p->siren_w[0]; b.siren_b0 = p->siren_b[0]; b.last_w = p->last_w; b.w0 = d->w0_first;
+    b.dpre = w.dpre; b.dz16t = w.dz16t; b.loss_sum = loss_sum;
+    b.g_last_w = g->last_w; b.g_last_b = g->last_b; b.g_siren_b1 = g->siren_b[1]; b.g_siren_b2 = g->siren_b[2];
+    b.g_siren_w0 = g->siren_w[0]; b.g_siren_b0 = g->siren_b[0];
+    b.n = n; b.n_tiles = n_tiles; b.ZP = m.ZP; b.NZ = NZ;
+    b.stage_bytes = static_cast<uint32_t>(m.ZP) * 128u;
+    b.nstage = 0;
+    for (b.stage_dz = 1; b.stage_dz >= 0 && b.nstage == 0; --b.stage_dz) {
+      for (int ns = 12; ns >= 3; --ns)
+        if (static_cast<int>(bwd_smem_layout(ns, b.stage_bytes, m.ZP, b.stage_dz).total) <= kSmemBudget) { b.nstage = ns; break; }
+      if (b.nstage) break;
+    }
+    NVP_CHECK(b.nstage >= 2, "latent too wide for the shared-memory plan of the tensor-core backward");
     const size_t smem = bwd_smem_layout(b.nstage, b.stage_bytes, m.ZP, b.stage_dz).total + 1024;
     NVP_CUDA(cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ScopedKernelTimer timer(K_MLP_BWD, st);
@@ -1292,7 +1325,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
     WgArgs wa{};
     wa.dpre = w.dpre; wa.stash = w.stash; wa.z16t = w.z16t; wa.gscale = w.gscale;
     for (int i = 0; i < 3; ++i) { wa.g_mod_w[i] = g->mod_w[i]; wa.g_mod_b[i] = g->mod_b[i]; wa.g_siren_w[i] = g->siren_w[i]; }
-    wa.n_units = 2 * n_tiles; wa.KZ = m.KZ; wa.Z = m.Z; wa.ZP = m.ZP;
+    wa.n_units = 2 * n_tiles; wa.stash_slots = fused ? static_cast<int>(FS_COUNT) : static_cast<int>(SL_COUNT); wa.KZ = m.KZ; wa.Z = m.Z; wa.ZP = m.ZP;
     build_wgrad_plan(wa, num_sms() - comm_sms);
     int max_hp = 0;
     for (int k = 0; k < wa.n_kinds; ++k) max_hp = std::max(max_hp, wa.kind[k].n_hp);
