@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnvp_b200.so")
+# NVP_B200_LIB: load another build of the library (development: ablation builds of scripts/fused_ablate.sh)
+LIB_PATH = os.environ.get("NVP_B200_LIB") or os.path.join(_HERE, "libnvp_b200.so")
 
 NVP_MAX_LEVELS = 32
 NVP_MAX_LAYERS = 3

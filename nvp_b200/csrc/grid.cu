@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(kGridThreads) grid_gather_kernel(const GridArg
     put(l * F2, fxy);
     put(pw + l * F2, fyt);
     put(2 * pw + l * F2, fxt);
-    // padding columns [Z, ZP): column Z carries the constant 1 (bias-gradient column of the wgrad GEMM;
-    // the matching forward weight columns are zero), the rest are zero.
+    // padding columns [Z, ZP): columns Z and Z+1 carry the constant 1 (bias-gradient column of the wgrad GEMM; the fused
+    // kernel's forward weight panels hold the modulator bias there, split hi + lo in fp16), the rest are zero.
     const int zdim = 3 * pw + 9 * F3;
     for (int c = zdim + l; c < a.kz * 64; c += L)
       *reinterpret_cast<__half*>(tbase + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63)) =
-          __float2half_rn(c == zdim ? 1.0f : 0.0f);
+          __float2half_rn((c == zdim || c == zdim + 1) ? 1.0f : 0.0f);
   }
 
   // 3x3 neighbourhood of the nearest voxel (same t slice), all weights 1.
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kCoarseGatherThreads) gather_coarse_kernel(con
   }
 }
 
-// 3x3 neighbourhood of the nearest voxel + padding columns (constant 1 at column Z, then zeros) of one latent row,
+// 3x3 neighbourhood of the nearest voxel + padding columns (constant 1 at columns Z and Z+1, then zeros) of one latent row,
 // assembled in registers and written as whole 16-byte chunks (c0 = first voxel column = 3*L*F2, chunk aligned).
 template <int F3>
 __device__ __forceinline__ void sparse_pad_sample(const GridArgs& a, int c0, int64_t s) {
@@ -597,7 +597,7 @@ __device__ __forceinline__ void sparse_pad_sample(const GridArgs& a, int c0, int
   const int r = static_cast<int>(s & 127);
   uint8_t* tbase = a.z16t + tile * a.kz * tc::kPanelBytes;
   constexpr int NV = 9 * F3;                 // voxel features
-  constexpr int NCH = (NV + 1 + 7) / 8;      // chunks holding features + the constant-1 column
+  constexpr int NCH = (NV + 2 + 7) / 8;      // chunks holding features + the two constant-1 columns
   auto chunk_ptr = [&](int c) {
     return reinterpret_cast<uint4*>(tbase + (c >> 6) * tc::kPanelBytes + tc::panel_chunk_offset(r, (c & 63) >> 3));
   };
@@ -613,7 +613,7 @@ __device__ __forceinline__ void sparse_pad_sample(const GridArgs& a, int c0, int
   const int vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
   float vals[NCH * 8];
 #pragma unroll
-  for (int i = 0; i < NCH * 8; ++i) vals[i] = (i == NV) ? 1.0f : 0.0f;
+  for (int i = 0; i < NCH * 8; ++i) vals[i] = (i == NV || i == NV + 1) ? 1.0f : 0.0f;
 #pragma unroll
   for (int v = 0; v < 9; ++v) {
     const int di = v / 3 - 1, dj = v - (v / 3) * 3 - 1;

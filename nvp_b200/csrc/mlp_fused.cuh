@@ -30,8 +30,11 @@
 //                                      H1: h1 -> dm1      A1: a1 -> v/dm2 -> z of the NEXT tile (Z and A1 swap roles)
 #pragma once
 
-constexpr int kFThreads = 384;
-constexpr int kFEpiThreads = 256;
+constexpr int kFEpiWarps = 16;
+constexpr int kFEpiThreads = kFEpiWarps * 32;
+constexpr int kFThreads = 128 + kFEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-3 reducers, warps 4-19 epilogue
+constexpr int kFCols = 256 / kFEpiWarps;        // columns of a 64-column panel one epilogue thread owns (16)
+constexpr int kFSub = 64 / kFCols;              // epilogue warps per TMEM lane quarter (4)
 constexpr int kFStages = 3;
 constexpr int kFPanelsPerTile = 28;
 constexpr uint32_t kFBuf = 2u * kPanelBytes;   // one [128 x 128] fp16 operand tile
@@ -42,18 +45,15 @@ enum {
   FB_WFULL = 0, FB_WEMPTY = 3, FB_ZFULL = 6,
   FB_AF_P0 = 7, FB_AF_P1, FB_AF_P2, FB_AF_P4, FB_AF_P5, FB_AF_P6,
   FB_PD_P0 = 13, FB_PD_P1 = 15, FB_PD_P3 = 17, FB_PD_P4 = 19, FB_PD_P5 = 21,
-  FB_TF_P0 = 23, FB_TF_P4, FB_G2_DONE, FB_DM2_STORED, FB_RD_A2, FB_RD_DSP2, FB_RD_DSP1, FB_RD_DSP0, FB_COUNT
+  FB_TF_P0 = 23, FB_TF_P4, FB_G2_DONE, FB_DM2_STORED, FB_A2_READY, FB_RD_A2, FB_RD_DSP2, FB_RD_DSP1, FB_RD_DSP0, FB_COUNT
 };
 
 struct FusedArgs {
   const uint8_t* wpk;      // 28 weight panels in stream order (see pack_fused_weights)
   const uint8_t* z16t;     // latent tiles [tile][2 panels]
   const float* tau;
-  const float* mod_b[3];
-  const float* siren_b[3];
-  const float* siren_w0;
-  const float* last_w;
-  const float* last_b;
+  int cslot;               // slot of g_fused_consts holding this call's epilogue constants (NVP_FCONST == 1)
+  const float* consts;     // the same FusedConsts staged in global memory
   float w0;
   const uint8_t* gt;       // loss mode (dout == NULL)
   const float* dout;       // explicit upstream gradient (nvp_backward)
@@ -68,28 +68,88 @@ struct FusedArgs {
   int n_tiles;
 };
 
+// Per-column constants of the epilogues.  They live in constant memory, not in shared memory: read through the constant
+// cache (LDC, address uniform over the warp) they cost no shared-memory bandwidth, which is what bounds the epilogue
+// phases (the first version read them with LDS.128 and spent a third of the shared-memory pipe on them).
+// The modulator biases are not here: they ride in the GEMMs (see pack_fused_weights).
+struct FusedConsts {
+  float bs[3][H];   // SIREN biases, layer 0 pre-multiplied by w0
+  float ws0[H];     // net.layers.0.weight, pre-multiplied by w0
+  float wl[3][H];   // net.last_layer.weight
+  float bl[4];      // net.last_layer.bias
+};
+constexpr int kFConstSlots = 8;   // rotating slots: up to 8 fused calls of one process may be in flight on a device
+__constant__ FusedConsts g_fused_consts[kFConstSlots];
+
+__global__ void fused_consts_kernel(FusedConsts* out, const float* b0, const float* b1, const float* b2, const float* w_first,
+                                    const float* last_w, const float* last_b, float w0) {
+  const int i = threadIdx.x;
+  if (i < H) {
+    out->bs[0][i] = __ldg(b0 + i) * w0; out->bs[1][i] = __ldg(b1 + i); out->bs[2][i] = __ldg(b2 + i);
+    out->ws0[i] = __ldg(w_first + i) * w0;
+    out->wl[0][i] = __ldg(last_w + i); out->wl[1][i] = __ldg(last_w + H + i); out->wl[2][i] = __ldg(last_w + 2 * H + i);
+  }
+  if (i < 4) out->bl[i] = i < 3 ? __ldg(last_b + i) : 0.0f;
+}
+
+// NVP_FCONST: where the epilogue reads its constants from.  0 = a copy in shared memory (LDS.128, address uniform over the
+// warp), 1 = constant memory (LDC).  Measured on B200: LDC with a register index is slower than the LDS it replaces
+// (P3 of the timeline: 2.5 K -> 3.5 K cycles), so shared memory is the default.
+#ifndef NVP_FCONST
+#define NVP_FCONST 0
+#endif
+// NVP_ABL: timing-only ablations for scripts/fused_ablate.sh (results are wrong when set):
+//   1 constants become literals   2 MUFU sin/cos become FMULs   4 no operand-tile stores   8 no TMEM loads
+//   16 idle reducers              32 no bulk stores to HBM
+#ifndef NVP_ABL
+#define NVP_ABL 0
+#endif
+#if NVP_ABL & 4
+#define F_STORE(...) do {} while (0)
+#else
+#define F_STORE(...) do { __VA_ARGS__; } while (0)
+#endif
+#if NVP_ABL & 8
+#define F_TLOAD(...) do {} while (0)
+#else
+#define F_TLOAD(...) do { __VA_ARGS__; } while (0)
+#endif
+#if NVP_ABL & 32
+#define F_BULK(...) do {} while (0)
+#else
+#define F_BULK(...) do { __VA_ARGS__; } while (0)
+#endif
+#if NVP_ABL & 1
+#define KC(x) 0.37f
+#else
+#define KC(x) (x)
+#endif
+
 struct FusedSmem { uint32_t bufs, ring, consts, rowdata, xch, bars, tmem, total; };
 __host__ __device__ constexpr FusedSmem fused_smem_layout() {
   FusedSmem s{};
   uint32_t o = 0;
   s.bufs = o; o += 5u * kFBuf;
   s.ring = o; o += kFStages * kPanelBytes;
-  s.consts = o; o += (10 * H + 4) * 4;   // bm[3][H] bs[3][H] (layer 0 times w0) ws0[H] (times w0) wl[3][H] bl[3]
+  s.consts = o; o += (sizeof(FusedConsts) + 15) / 16 * 16;
   s.rowdata = o; o += kTile * 16;        // per row: drgb0..2 (times gs), tau
-  s.xch = o; o += 2 * kTile * 16;        // partial rgb of the two column halves
+  s.xch = o; o += kFSub * kTile * 16;    // partial rgb of the column slices
   s.bars = o; o += 64 * 8;
   s.tmem = o; o += 16;
   s.total = o;
   return s;
 }
 
-#ifdef NVP_FUSED_REDUCED_SIN
+#if NVP_ABL & 2
+__device__ __forceinline__ float f_sin(float x) { return x * 0.5f; }
+__device__ __forceinline__ void f_sincos(float x, float& s, float& c) { s = x * 0.5f; c = x * 0.25f; }
+#elif defined(NVP_FUSED_REDUCED_SIN)
 __device__ __forceinline__ float f_sin(float x) { return fast_sin<true>(x); }
 __device__ __forceinline__ void f_sincos(float x, float& s, float& c) { fast_sincos(x, s, c); }
 #else
 // sin.approx / cos.approx: FMUL.RZ by 1/2pi + MUFU, which takes its argument in revolutions and drops the integer part
-// itself; the only loss against a Cody-Waite reduction is the rounding of that product (|x| * 2^-24, i.e. 4e-6 at the
-// |30 (w t + b)| <= 60 of SIREN layer 0; scripts/sin_probe.cu measures it).
+// itself; the only loss against a Cody-Waite reduction is the rounding of that product: measured max error 1.4e-7 |x|
+// (8.6e-6 at the |30 (w t + b)| <= 60 of SIREN layer 0; scripts/sin_probe.cu, profiles/r02_sin_probe.txt).
 __device__ __forceinline__ float f_sin(float x) { return __sinf(x); }
 __device__ __forceinline__ void f_sincos(float x, float& s, float& c) { __sincosf(x, &s, &c); }
 #endif
@@ -108,35 +168,40 @@ __device__ __forceinline__ void load_rown(const uint8_t* panel, int r, int c0, f
     }
   }
 }
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+template <int N>
+__device__ __forceinline__ void store_packed(uint8_t* panel, int r, int c0, const uint32_t (&v)[N / 2]) {
+#pragma unroll
+  for (int j = 0; j < N / 8; ++j)
+    *reinterpret_cast<uint4*>(panel + panel_chunk_offset(r, (c0 >> 3) + j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr FusedSmem L = fused_smem_layout();
+  constexpr int C = kFCols;
   uint8_t* bufs = smem + L.bufs;
   uint8_t* ring = smem + L.ring;
-  float* s_bm = reinterpret_cast<float*>(smem + L.consts);   // [3][H]
-  float* s_bs = s_bm + 3 * H;                                // [3][H], layer 0 pre-multiplied by w0
-  float* s_ws0 = s_bm + 6 * H;                               // [H], pre-multiplied by w0
-  float* s_wl = s_bm + 7 * H;                                // [3][H]
-  float* s_bl = s_bm + 10 * H;                               // [3]
+#if NVP_FCONST == 1
+  const FusedConsts& K = g_fused_consts[a.cslot];
+#else
+  const FusedConsts& K = *reinterpret_cast<const FusedConsts*>(smem + L.consts);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(FusedConsts) / 4); i += kFThreads)
+    reinterpret_cast<float*>(smem + L.consts)[i] = __ldg(a.consts + i);
+#endif
   float4* s_row = reinterpret_cast<float4*>(smem + L.rowdata);
   float4* s_xch = reinterpret_cast<float4*>(smem + L.xch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 3 * H; i += kFThreads) {
-    s_bm[i] = __ldg(a.mod_b[i / H] + (i % H));
-    s_bs[i] = __ldg(a.siren_b[i / H] + (i % H)) * (i < H ? a.w0 : 1.0f);
-    s_wl[i] = __ldg(a.last_w + i);
-  }
-  for (int i = tid; i < H; i += kFThreads) s_ws0[i] = __ldg(a.siren_w0 + i) * a.w0;
-  if (tid < 3) s_bl[tid] = __ldg(a.last_b + tid);
   if (tid == 0) {
     for (int i = 0; i < FB_COUNT; ++i) {
       uint32_t cnt = 1;
-      if (i == FB_TF_P0 || i == FB_TF_P4) cnt = kFEpiThreads / 32;
+      if (i == FB_TF_P0 || i == FB_TF_P4) cnt = kFEpiWarps;
+      if (i == FB_A2_READY) cnt = kTile;
       if (i >= FB_RD_A2 && i <= FB_RD_DSP0) cnt = 2;
       mbar_init(&bars[i], cnt);
     }
@@ -193,10 +258,19 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTile, H, false, false);
       uint32_t g = 0;
+#ifdef NVP_TIMELINE
+      long long ring_wait = 0;
+#endif
       // one 64-wide K panel: A = panel `ap` of a shared-memory tile, B = next ring stage, D = TMEM slot `acc`
       auto gemm = [&](const uint8_t* ap, uint32_t acc, bool accumulate) {
         const uint32_t st = g % kFStages, ph = (g / kFStages) & 1;
+#ifdef NVP_TIMELINE
+        const long long t0 = clock64();
+#endif
         mbar_wait(&bars[FB_WFULL + st], ph);
+#ifdef NVP_TIMELINE
+        ring_wait += clock64() - t0;
+#endif
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(ap), b_addr = smem_u32(ring + st * kPanelBytes);
 #pragma unroll
@@ -218,6 +292,9 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         uint8_t* const bZ = buf_z(it);
         uint8_t* const bA1 = buf_a1(it);
         const uint32_t P = kPanelBytes;
+#ifdef NVP_TIMELINE
+        if (it == 3) ring_wait = 0;
+#endif
         // ---- F1: m1 -> S0, sp1 -> S1 ----
         NVP_TL(it == 3, 64);
         gemm(bZ, S0, false); gemm(bZ + P, S0, true);
@@ -227,6 +304,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 65);
         gemm(bH0 + P, S0, true); gemm(bA0 + P, S1, true);
         umma_commit(&bars[FB_AF_P1]);
+        NVP_TL(it == 3, 80);
         // ---- F2: m2 -> S2, sp2 -> S3 ----
         gemm(bZ, S2, false); gemm(bZ + P, S2, true);
         wait_pd(FB_PD_P1 + 0, par);
@@ -235,26 +313,29 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 66);
         gemm(bH1 + P, S2, true); gemm(bA1 + P, S3, true);
         umma_commit(&bars[FB_AF_P2]);
-        // ---- G2: da1 = dsp2 Ws2 -> S0, dh1 = dm2 W2h -> S2, dz = dm2 W2z -> S3 (dsp2 in A0, dm2 in A1) ----
+        NVP_TL(it == 3, 81);
+        // ---- G2: da1 = dsp2 Ws2 -> S0, dh1 = dm2 W2h -> S2 (dsp2 in A0, dm2 in A1); then dz = dm2 W2z -> S3 ----
         wait_pd(FB_PD_P3 + 0, par);
         NVP_TL(it == 3, 67);
-        gemm(bA0, S0, false); gemm(bA1, S2, false); gemm(bA1, S3, false);
+        gemm(bA0, S0, false); gemm(bA1, S2, false);
         wait_pd(FB_PD_P3 + 1, par);
         NVP_TL(it == 3, 68);
         gemm(bA0 + P, S0, true); gemm(bA1 + P, S2, true);
         umma_commit(&bars[FB_AF_P4]);
-        gemm(bA1 + P, S3, true);
+        NVP_TL(it == 3, 82);
+        gemm(bA1, S3, false); gemm(bA1 + P, S3, true);
         umma_commit(&bars[FB_G2_DONE]);
-        // ---- G1: da0 = dsp1 Ws1 -> S0, dh0 = dm1 W1h -> S2, dz += dm1 W1z (dsp1 in Z, dm1 in H1) ----
+        // ---- G1: da0 = dsp1 Ws1 -> S0, dh0 = dm1 W1h -> S2 (dsp1 in Z, dm1 in H1); then dz += dm1 W1z ----
         // S0 / S2 are still read by P4 until it has loaded its last panel from TMEM (FB_TF_P4)
         wait_pd(FB_PD_P4 + 0, par); wait_pd(FB_TF_P4, par);
         NVP_TL(it == 3, 69);
-        gemm(bZ, S0, false); gemm(bH1, S2, false); gemm(bH1, S3, true);
+        gemm(bZ, S0, false); gemm(bH1, S2, false);
         wait_pd(FB_PD_P4 + 1, par);
         NVP_TL(it == 3, 70);
         gemm(bZ + P, S0, true); gemm(bH1 + P, S2, true);
         umma_commit(&bars[FB_AF_P5]);
-        gemm(bH1 + P, S3, true);
+        NVP_TL(it == 3, 83);
+        gemm(bH1, S3, true); gemm(bH1 + P, S3, true);
         // ---- G0 (dz += dm0 W0z, dm0 in H0) around F0 of the next tile (m0 -> S1, free since FB_TF_P4) ----
         wait_pd(FB_PD_P5 + 0, par);
         NVP_TL(it == 3, 71);
@@ -268,6 +349,9 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 72);
         gemm(bH0 + P, S3, true);
         umma_commit(&bars[FB_AF_P6]);
+#ifdef NVP_TIMELINE
+        if (it == 3 && blockIdx.x == 0) g_timeline[90] = static_cast<unsigned long long>(ring_wait);
+#endif
       }
     }
   } else if (warp < 4) {
@@ -282,14 +366,15 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
     auto ldx = [&](const uint8_t* tile, int r) {
       const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + poff + static_cast<uint32_t>(r) * 128u +
                                                             ((lane_chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4) + lane_off);
-      return __half22float2(*reinterpret_cast<const __half2*>(&v));
+      return unpack_half2(v);
     };
     auto arrive = [&](int bar) { __syncwarp(); if (lane == 0) mbar_arrive(&bars[bar]); };
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const uint8_t* const bZ = buf_z(it);
-      mbar_wait(&bars[FB_PD_P3 + 0], par);   // a2 (both panels), the per-row data and dsp2 panel 0 are in place
-#pragma unroll 8
+      mbar_wait(&bars[FB_A2_READY], par);   // a2 (both panels) and the per-row drgb / tau are in place
+#if !(NVP_ABL & 16)
+#pragma unroll 4
       for (int r = 0; r < kTile; ++r) {
         const float2 x = ldx(bZ, r);
         const float4 d = s_row[r];
@@ -297,24 +382,35 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         wl1a = fmaf(d.y, x.x, wl1a); wl1b = fmaf(d.y, x.y, wl1b);
         wl2a = fmaf(d.z, x.x, wl2a); wl2b = fmaf(d.z, x.y, wl2b);
       }
+#endif
       arrive(FB_RD_A2);
-      if (w == 1) mbar_wait(&bars[FB_PD_P3 + 1], par);
-#pragma unroll 8
+      NVP_TL(w == 0 && lane == 0 && it == 3, 48);
+      mbar_wait(&bars[FB_PD_P3 + w], par);
+#if !(NVP_ABL & 16)
+#pragma unroll 4
       for (int r = 0; r < kTile; ++r) { const float2 x = ldx(bA0, r); b2a += x.x; b2b += x.y; }
+#endif
       arrive(FB_RD_DSP2);
+      NVP_TL(w == 0 && lane == 0 && it == 3, 49);
       mbar_wait(&bars[FB_PD_P4 + w], par);
-#pragma unroll 8
+#if !(NVP_ABL & 16)
+#pragma unroll 4
       for (int r = 0; r < kTile; ++r) { const float2 x = ldx(bZ, r); b1a += x.x; b1b += x.y; }
+#endif
       arrive(FB_RD_DSP1);
+      NVP_TL(w == 0 && lane == 0 && it == 3, 50);
       mbar_wait(&bars[FB_PD_P5 + w], par);
-#pragma unroll 8
+#if !(NVP_ABL & 16)
+#pragma unroll 4
       for (int r = 0; r < kTile; ++r) {
         const float2 x = ldx(bA0, r);
         const float t = s_row[r].w;
         b0a += x.x; b0b += x.y;
         w0a = fmaf(t, x.x, w0a); w0b = fmaf(t, x.y, w0b);
       }
+#endif
       arrive(FB_RD_DSP0);
+      NVP_TL(w == 0 && lane == 0 && it == 3, 51);
     }
     if (my_tiles > 0) {
       const float inv_gs = __ldg(a.gscale + 1);
@@ -334,26 +430,15 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
   } else {
     // ================= epilogue warps =================
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    const int sub = (warp - 4) >> 2;            // which 32-column half of the current 64-column panel
+    const int sub = (warp - 4) >> 2;            // which C-column slice of the current 64-column panel
     const int r = quarter * 32 + lane;          // row inside the tile
-    const int pc = sub * 32;                    // first column inside the panel
+    const int pc = sub * C;                     // first column inside the panel
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const bool elected = (tid == 128);
     const float gs = __ldg(a.gscale), inv_gs = __ldg(a.gscale + 1), loss_mult = __ldg(a.gscale + 2);
     float loss_acc = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f;
 
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kFEpiThreads) : "memory"); };
-    // start of a phase: the accumulators are complete; every earlier bulk store has left its shared-memory source
-    // and the reducers are done with the tile this phase overwrites (rd_bar >= 0) before anybody writes
-    auto phase_begin = [&](int af_bar, uint32_t par, int rd_bar, uint32_t rd_par, bool rd_wait) {
-      mbar_wait(&bars[af_bar], par);
-      tcgen05_fence_after();
-      if (elected) {
-        bulk_wait_read0();
-        if (rd_wait) mbar_wait(&bars[rd_bar], rd_par);
-      }
-      epi_sync();
-    };
     // end of a panel: operand tiles visible to the async proxy, then one thread releases the MMA warp and hands the
     // panel(s) to the TMA for the weight-gradient kernel
     auto panel_end = [&](int pd_bar, uint8_t* dst0, const uint8_t* src0, uint8_t* dst1, const uint8_t* src1) {
@@ -362,118 +447,146 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       epi_sync();
       if (elected) {
         mbar_arrive(&bars[pd_bar]);
-        if (dst0) bulk_s2g(dst0, src0, kPanelBytes);
-        if (dst1) bulk_s2g(dst1, src1, kPanelBytes);
+        F_BULK(if (dst0) bulk_s2g(dst0, src0, kPanelBytes));
+        F_BULK(if (dst1) bulk_s2g(dst1, src1, kPanelBytes));
         bulk_commit();
       }
     };
     auto tmem_release = [&](int bar) { tcgen05_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&bars[bar]); };
+    auto wait_acc = [&](int af_bar, uint32_t par) { mbar_wait(&bars[af_bar], par); tcgen05_fence_after(); };
 
+    float tau = 0.f;
+    {
+      const int64_t s0 = static_cast<int64_t>(tile_of(0)) * kTile + r;
+      if (my_tiles > 0 && s0 < a.n) tau = __ldg(a.tau + s0);
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const int tile = tile_of(it);
       const int64_t s = static_cast<int64_t>(tile) * kTile + r;
       const bool valid = s < a.n;
-      const float tau = valid ? __ldg(a.tau + s) : 0.0f;
       uint8_t* const bZ = buf_z(it);
       uint8_t* const bA1 = buf_a1(it);
       uint8_t* const st_base = a.stash + static_cast<size_t>(tile) * FS_COUNT * kFBuf;
       uint8_t* const dp_base = a.dpre + static_cast<size_t>(tile) * DP_COUNT * kFBuf;
       auto st_dst = [&](int slot, int p) { return st_base + static_cast<size_t>(slot) * kFBuf + static_cast<size_t>(p) * kPanelBytes; };
       auto dp_dst = [&](int slot, int p) { return dp_base + static_cast<size_t>(slot) * kFBuf + static_cast<size_t>(p) * kPanelBytes; };
+      // ground truth of my row, fetched a few phases before it is needed
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      if (valid && a.dout == nullptr) {
+        g0 = (static_cast<float>(__ldg(a.gt + s * 3)) - 127.5f) / 127.5f;
+        g1 = (static_cast<float>(__ldg(a.gt + s * 3 + 1)) - 127.5f) / 127.5f;
+        g2 = (static_cast<float>(__ldg(a.gt + s * 3 + 2)) - 127.5f) / 127.5f;
+      }
 
       // ---------------- P0: h0 = lrelu(m0 + b), a0 = sin(w0 (w tau + b)) h0 ----------------
       // writes H0 (dm0 of the previous tile: read by G0, done) and A0 (dsp0 of the previous tile: reducers)
-      phase_begin(FB_AF_P0, par, FB_RD_DSP0, par ^ 1, it > 0);
+      wait_acc(FB_AF_P0, par);
       NVP_TL(elected && it == 3, 0);
+      NVP_TL(elected && it == 4, 14);
+      if (elected) {
+        bulk_wait_read<1>();   // all earlier bulk stores but the newest (dz, from the Z buffer) have left shared memory
+        if (it > 0) mbar_wait(&bars[FB_RD_DSP0], par ^ 1);
+      }
+      epi_sync();
+      NVP_TL(elected && it == 3, 16);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
         const int col = p * 64 + pc;
-        uint32_t vm[32];
-        tmem_ld32(S1 + lane_base + col, vm);
+        uint32_t vm[C] = {};
+        F_TLOAD(tmem_ldn<C>(S1 + lane_base + col, vm));
         tmem_ld_wait();
         if (p == 1) tmem_release(FB_TF_P0);   // S1 may now receive sp1
-        float hv[32], av[32];
+        float hv[C], av[C];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[col + i]);
-          av[i] = f_sin(fmaf(tau, s_ws0[col + i], s_bs[col + i])) * hv[i];
+        for (int i = 0; i < C; ++i) {
+          hv[i] = lrelu(__uint_as_float(vm[i]));   // the bias came with the GEMM
+          av[i] = f_sin(fmaf(tau, KC(K.ws0[col + i]), KC(K.bs[0][col + i]))) * hv[i];
         }
-        store_row32(bH0 + p * kPanelBytes, r, pc, hv);
-        store_row32(bA0 + p * kPanelBytes, r, pc, av);
+        F_STORE(store_rown<C>(bH0 + p * kPanelBytes, r, pc, hv));
+        F_STORE(store_rown<C>(bA0 + p * kPanelBytes, r, pc, av));
         panel_end(FB_PD_P0 + p, st_dst(FS_H0, p), bH0 + p * kPanelBytes, st_dst(FS_A0, p), bA0 + p * kPanelBytes);
       }
       NVP_TL(elected && it == 3, 1);
 
       // ---------------- P1: h1 = lrelu(m1 + b), a1 = sin(sp1 + b) h1 ----------------
-      phase_begin(FB_AF_P1, par, 0, 0, false);
+      // writes H1 (dm1 of the previous tile) and A1 (= the previous tile's Z buffer: its dz store must have left)
+      wait_acc(FB_AF_P1, par);
       NVP_TL(elected && it == 3, 2);
+      if (elected) bulk_wait_read<2>();
+      epi_sync();
+      NVP_TL(elected && it == 3, 17);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
         const int col = p * 64 + pc;
-        uint32_t vm[32], vs[32];
-        tmem_ld32(S0 + lane_base + col, vm);
-        tmem_ld32(S1 + lane_base + col, vs);
+        uint32_t vm[C] = {}, vs[C] = {};
+        F_TLOAD(tmem_ldn<C>(S0 + lane_base + col, vm));
+        F_TLOAD(tmem_ldn<C>(S1 + lane_base + col, vs));
         tmem_ld_wait();
-        float hv[32], av[32];
+        float hv[C], av[C];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          hv[i] = lrelu(__uint_as_float(vm[i]) + s_bm[H + col + i]);
-          av[i] = f_sin(__uint_as_float(vs[i]) + s_bs[H + col + i]) * hv[i];
+        for (int i = 0; i < C; ++i) {
+          hv[i] = lrelu(__uint_as_float(vm[i]));
+          av[i] = f_sin(__uint_as_float(vs[i]) + KC(K.bs[1][col + i])) * hv[i];
         }
-        store_row32(bH1 + p * kPanelBytes, r, pc, hv);
-        store_row32(bA1 + p * kPanelBytes, r, pc, av);
+        F_STORE(store_rown<C>(bH1 + p * kPanelBytes, r, pc, hv));
+        F_STORE(store_rown<C>(bA1 + p * kPanelBytes, r, pc, av));
         panel_end(FB_PD_P1 + p, st_dst(FS_H1, p), bH1 + p * kPanelBytes, st_dst(FS_A1, p), bA1 + p * kPanelBytes);
       }
       NVP_TL(elected && it == 3, 3);
 
-      // ---------------- P2: layer 2 forward; keeps u = h2 cos2 (A0) and v = sin2 lrelu'(m2) (A1), a2 (Z) ----------------
-      phase_begin(FB_AF_P2, par, 0, 0, false);
+      // ---------------- P2: layer 2 forward.  a2 -> Z (for the reducers); u = h2 cos2 and v = sin2 lrelu'(m2) stay in
+      // registers (packed fp16) until drgb is known ----------------
+      wait_acc(FB_AF_P2, par);   // all MMAs reading z, a0, a1 have completed
       NVP_TL(elected && it == 3, 4);
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-#pragma unroll 1
+      uint32_t upk[2][C / 2], vpk[2][C / 2];
+#pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int col = p * 64 + pc;
-        uint32_t vm[32], vs[32];
-        tmem_ld32(S2 + lane_base + col, vm);
-        tmem_ld32(S3 + lane_base + col, vs);
+        uint32_t vm[C] = {}, vs[C] = {};
+        F_TLOAD(tmem_ldn<C>(S2 + lane_base + col, vm));
+        F_TLOAD(tmem_ldn<C>(S3 + lane_base + col, vs));
         tmem_ld_wait();
-        float x0[32], x1[32];
+        uint32_t apk[C / 2];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float m = __uint_as_float(vm[i]) + s_bm[2 * H + col + i];
-          const float hh = lrelu(m);
-          float sn, cs;
-          f_sincos(__uint_as_float(vs[i]) + s_bs[2 * H + col + i], sn, cs);
-          const float a2 = sn * hh;
-          rgb0 = fmaf(a2, s_wl[col + i], rgb0);
-          rgb1 = fmaf(a2, s_wl[H + col + i], rgb1);
-          rgb2 = fmaf(a2, s_wl[2 * H + col + i], rgb2);
-          x0[i] = a2;
-          x1[i] = hh * cs;                                   // u
-          vm[i] = __float_as_uint(sn * (m > 0.f ? 1.0f : 0.01f));   // v
+        for (int i = 0; i < C; i += 2) {
+          float a2[2], uu[2], vv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float m = __uint_as_float(vm[i + e]);
+            const float hh = lrelu(m);
+            float sn, cs;
+            f_sincos(__uint_as_float(vs[i + e]) + KC(K.bs[2][col + i + e]), sn, cs);
+            a2[e] = sn * hh;
+            rgb0 = fmaf(a2[e], KC(K.wl[0][col + i + e]), rgb0);
+            rgb1 = fmaf(a2[e], KC(K.wl[1][col + i + e]), rgb1);
+            rgb2 = fmaf(a2[e], KC(K.wl[2][col + i + e]), rgb2);
+            uu[e] = hh * cs;
+            vv[e] = sn * (m > 0.f ? 1.0f : 0.01f);
+          }
+          apk[i / 2] = pack_half2(a2[0], a2[1]);
+          upk[p][i / 2] = pack_half2(uu[0], uu[1]);
+          vpk[p][i / 2] = pack_half2(vv[0], vv[1]);
         }
-        store_row32(bZ + p * kPanelBytes, r, pc, x0);
-        store_row32(bA0 + p * kPanelBytes, r, pc, x1);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x0[i] = __uint_as_float(vm[i]);
-        store_row32(bA1 + p * kPanelBytes, r, pc, x0);
+        F_STORE(store_packed<C>(bZ + p * kPanelBytes, r, pc, apk));
       }
-      // rgb of my row = my half of the columns + the other warp's half
+      // rgb of my row = the sum over the column slices
       s_xch[sub * kTile + r] = make_float4(rgb0, rgb1, rgb2, 0.f);
+      if (elected) bulk_wait_read<0>();   // the a0 / a1 stores have left A0 / A1 long ago: P3 writes there
       epi_sync();
-      {
-        const float4 o = s_xch[(sub ^ 1) * kTile + r];
-        rgb0 += o.x + s_bl[0]; rgb1 += o.y + s_bl[1]; rgb2 += o.z + s_bl[2];
+#pragma unroll
+      for (int q = 1; q < kFSub; ++q) {
+        const float4 o = s_xch[((sub + q) % kFSub) * kTile + r];
+        rgb0 += o.x; rgb1 += o.y; rgb2 += o.z;
       }
+      rgb0 += KC(K.bl[0]); rgb1 += KC(K.bl[1]); rgb2 += KC(K.bl[2]);
       float d0 = 0.f, d1 = 0.f, d2 = 0.f;
       if (valid) {
         if (a.dout != nullptr) {
           d0 = __ldg(a.dout + s * 3) * gs; d1 = __ldg(a.dout + s * 3 + 1) * gs; d2 = __ldg(a.dout + s * 3 + 2) * gs;
         } else {
-          const float e0 = rgb0 - (static_cast<float>(__ldg(a.gt + s * 3)) - 127.5f) / 127.5f;
-          const float e1 = rgb1 - (static_cast<float>(__ldg(a.gt + s * 3 + 1)) - 127.5f) / 127.5f;
-          const float e2 = rgb2 - (static_cast<float>(__ldg(a.gt + s * 3 + 2)) - 127.5f) / 127.5f;
+          const float e0 = rgb0 - g0, e1 = rgb1 - g1, e2 = rgb2 - g2;
           if (sub == 0) loss_acc += e0 * e0 + e1 * e1 + e2 * e2;
           d0 = e0 * loss_mult; d1 = e1 * loss_mult; d2 = e2 * loss_mult;
         }
@@ -482,115 +595,140 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       if (sub == 0) {
         gb0 += d0; gb1 += d1; gb2 += d2;
         s_row[r] = make_float4(d0, d1, d2, tau);
+        mbar_arrive(&bars[FB_A2_READY]);    // releases my a2 / row data (and, through the barrier above, everybody's a2)
       }
       NVP_TL(elected && it == 3, 5);
 
-      // ---------------- P3: da2 = drgb Wl ; dsp2 = da2 u (A0) ; dm2 = da2 v (A1) ----------------
-#pragma unroll 1
+      // ---------------- P3: da2 = drgb Wl ; dsp2 = da2 u -> A0 ; dm2 = da2 v -> A1 ----------------
+#pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int col = p * 64 + pc;
-        float u[32], da[32];
-        load_rown<32>(bA0 + p * kPanelBytes, r, pc, u);
+        uint32_t o1[C / 2], o2[C / 2];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          da[i] = d0 * s_wl[col + i] + d1 * s_wl[H + col + i] + d2 * s_wl[2 * H + col + i];
-          u[i] *= da[i];
+        for (int i = 0; i < C; i += 2) {
+          const float da0 = d0 * KC(K.wl[0][col + i]) + d1 * KC(K.wl[1][col + i]) + d2 * KC(K.wl[2][col + i]);
+          const float da1 = d0 * KC(K.wl[0][col + i + 1]) + d1 * KC(K.wl[1][col + i + 1]) + d2 * KC(K.wl[2][col + i + 1]);
+          const float2 uu = unpack_half2(upk[p][i / 2]), vv = unpack_half2(vpk[p][i / 2]);
+          o1[i / 2] = pack_half2(da0 * uu.x, da1 * uu.y);
+          o2[i / 2] = pack_half2(da0 * vv.x, da1 * vv.y);
         }
-        store_row32(bA0 + p * kPanelBytes, r, pc, u);
-        load_rown<32>(bA1 + p * kPanelBytes, r, pc, u);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) u[i] *= da[i];
-        store_row32(bA1 + p * kPanelBytes, r, pc, u);
+        F_STORE(store_packed<C>(bA0 + p * kPanelBytes, r, pc, o1));
+        F_STORE(store_packed<C>(bA1 + p * kPanelBytes, r, pc, o2));
         panel_end(FB_PD_P3 + p, dp_dst(DP_S2, p), bA0 + p * kPanelBytes, dp_dst(DP_M2, p), bA1 + p * kPanelBytes);
       }
       NVP_TL(elected && it == 3, 6);
 
       // ---------------- P4: dsp1 = da1 h1 cos1 (Z, over a2) ; dm1 = (dh1 + da1 sin1) lrelu'(h1) (H1, in place) ----------------
-      mbar_wait(&bars[FB_AF_P4], par);
-      tcgen05_fence_after();
+      wait_acc(FB_AF_P4, par);
+      NVP_TL(elected && it == 3, 8);
       if (elected) {
-        bulk_wait_read0();                        // dsp2 / dm2 have left A0 / A1 ...
+        bulk_wait_read<0>();                      // dsp2 / dm2 have left A0 / A1 ...
         mbar_arrive(&bars[FB_DM2_STORED]);        // ... so the producer may load the next latent tile over dm2
         mbar_wait(&bars[FB_RD_A2], par);          // the reducers are done with a2
       }
       epi_sync();
-      NVP_TL(elected && it == 3, 8);
+      NVP_TL(elected && it == 3, 18);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          const int c16 = pc + ch * 16, col = p * 64 + c16;
-          uint32_t va[16], vh[16], vs[16];
-          tmem_ld16(S0 + lane_base + col, va);
-          tmem_ld16(S2 + lane_base + col, vh);
-          tmem_ld16(S1 + lane_base + col, vs);
-          float hv[16], o[16];
-          load_rown<16>(bH1 + p * kPanelBytes, r, c16, hv);
-          tmem_ld_wait();
-          if (p == 1 && ch == 1) tmem_release(FB_TF_P4);   // S0 / S2 / S1 may be overwritten (G1, next tile's F0)
-          float q[16];
+        const int col = p * 64 + pc;
+        uint32_t va[C] = {}, vh[C] = {}, vs[C] = {};
+        F_TLOAD(tmem_ldn<C>(S0 + lane_base + col, va));
+        F_TLOAD(tmem_ldn<C>(S2 + lane_base + col, vh));
+        F_TLOAD(tmem_ldn<C>(S1 + lane_base + col, vs));
+        float hv[C];
+        load_rown<C>(bH1 + p * kPanelBytes, r, pc, hv);
+        tmem_ld_wait();
+        if (p == 1) tmem_release(FB_TF_P4);   // S0 / S2 / S1 may be overwritten (G1, next tile's F0)
+        uint32_t o1[C / 2], o2[C / 2];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < C; i += 2) {
+          float x[2], y[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
             float sn, cs;
-            f_sincos(__uint_as_float(vs[i]) + s_bs[H + col + i], sn, cs);
-            const float dav = __uint_as_float(va[i]);
-            o[i] = dav * hv[i] * cs;
-            q[i] = fmaf(dav, sn, __uint_as_float(vh[i])) * (hv[i] > 0.f ? 1.0f : 0.01f);
+            f_sincos(__uint_as_float(vs[i + e]) + KC(K.bs[1][col + i + e]), sn, cs);
+            const float dav = __uint_as_float(va[i + e]);
+            x[e] = dav * hv[i + e] * cs;
+            y[e] = fmaf(dav, sn, __uint_as_float(vh[i + e])) * (hv[i + e] > 0.f ? 1.0f : 0.01f);
           }
-          store_rown<16>(bZ + p * kPanelBytes, r, c16, o);
-          store_rown<16>(bH1 + p * kPanelBytes, r, c16, q);
+          o1[i / 2] = pack_half2(x[0], x[1]);
+          o2[i / 2] = pack_half2(y[0], y[1]);
         }
+        F_STORE(store_packed<C>(bZ + p * kPanelBytes, r, pc, o1));
+        F_STORE(store_packed<C>(bH1 + p * kPanelBytes, r, pc, o2));
         panel_end(FB_PD_P4 + p, dp_dst(DP_S1, p), bZ + p * kPanelBytes, dp_dst(DP_M1, p), bH1 + p * kPanelBytes);
       }
       NVP_TL(elected && it == 3, 9);
 
       // ---------------- P5: dsp0 = da0 h0 cos0 (A0, over dsp2) ; dm0 = (dh0 + da0 sin0) lrelu'(h0) (H0, in place) ----------------
-      phase_begin(FB_AF_P5, par, FB_RD_DSP2, par, true);
+      wait_acc(FB_AF_P5, par);
       NVP_TL(elected && it == 3, 10);
+      if (elected) {
+        bulk_wait_read<2>();                      // everything but P4's two groups (dsp1 / dm1, in Z / H1)
+        mbar_wait(&bars[FB_RD_DSP2], par);        // the reducers are done with dsp2
+      }
+      epi_sync();
+      NVP_TL(elected && it == 3, 19);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          const int c16 = pc + ch * 16, col = p * 64 + c16;
-          uint32_t va[16], vh[16];
-          tmem_ld16(S0 + lane_base + col, va);
-          tmem_ld16(S2 + lane_base + col, vh);
-          float hv[16], o[16], q[16];
-          load_rown<16>(bH0 + p * kPanelBytes, r, c16, hv);
-          tmem_ld_wait();
+        const int col = p * 64 + pc;
+        uint32_t va[C] = {}, vh[C] = {};
+        F_TLOAD(tmem_ldn<C>(S0 + lane_base + col, va));
+        F_TLOAD(tmem_ldn<C>(S2 + lane_base + col, vh));
+        float hv[C];
+        load_rown<C>(bH0 + p * kPanelBytes, r, pc, hv);
+        tmem_ld_wait();
+        uint32_t o1[C / 2], o2[C / 2];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < C; i += 2) {
+          float x[2], y[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
             float sn, cs;
-            f_sincos(fmaf(tau, s_ws0[col + i], s_bs[col + i]), sn, cs);
-            const float dav = __uint_as_float(va[i]);
-            o[i] = dav * hv[i] * cs;
-            q[i] = fmaf(dav, sn, __uint_as_float(vh[i])) * (hv[i] > 0.f ? 1.0f : 0.01f);
+            f_sincos(fmaf(tau, KC(K.ws0[col + i + e]), KC(K.bs[0][col + i + e])), sn, cs);
+            const float dav = __uint_as_float(va[i + e]);
+            x[e] = dav * hv[i + e] * cs;
+            y[e] = fmaf(dav, sn, __uint_as_float(vh[i + e])) * (hv[i + e] > 0.f ? 1.0f : 0.01f);
           }
-          store_rown<16>(bA0 + p * kPanelBytes, r, c16, o);
-          store_rown<16>(bH0 + p * kPanelBytes, r, c16, q);
+          o1[i / 2] = pack_half2(x[0], x[1]);
+          o2[i / 2] = pack_half2(y[0], y[1]);
         }
+        F_STORE(store_packed<C>(bA0 + p * kPanelBytes, r, pc, o1));
+        F_STORE(store_packed<C>(bH0 + p * kPanelBytes, r, pc, o2));
         panel_end(FB_PD_P5 + p, dp_dst(DP_M0, p), bH0 + p * kPanelBytes, nullptr, nullptr);
       }
       NVP_TL(elected && it == 3, 11);
+      // tau of the next tile's row (consumed at its P0, needed by the reducers until this tile's dsp0 sum is done:
+      // it only enters s_row at the next tile's P2)
+      {
+        const int64_t sn = s + static_cast<int64_t>(gridDim.x) * kTile;
+        tau = (it + 1 < my_tiles && sn < a.n) ? __ldg(a.tau + sn) : 0.0f;
+      }
 
       // ---------------- P6: dz -> fp16 tile staged in Z (over dsp1) -> HBM ----------------
-      phase_begin(FB_AF_P6, par, FB_RD_DSP1, par, true);
+      wait_acc(FB_AF_P6, par);
       NVP_TL(elected && it == 3, 12);
+      if (elected) {
+        bulk_wait_read<2>();                      // everything but P5's two groups (dm0, in H0)
+        mbar_wait(&bars[FB_RD_DSP1], par);        // the reducers are done with dsp1
+      }
+      epi_sync();
+      NVP_TL(elected && it == 3, 20);
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
-        uint32_t v[32];
-        float f[32];
-        tmem_ld32(S3 + lane_base + q * 64 + pc, v);
+        uint32_t v[C] = {};
+        float f[C];
+        F_TLOAD(tmem_ldn<C>(S3 + lane_base + q * 64 + pc, v));
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        store_row32(bZ + q * kPanelBytes, r, pc, f);
+        for (int i = 0; i < C; ++i) f[i] = __uint_as_float(v[i]);
+        F_STORE(store_rown<C>(bZ + q * kPanelBytes, r, pc, f));
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       epi_sync();
       if (elected) {
-        bulk_s2g(a.dz16t + static_cast<size_t>(tile) * kFBuf, bZ, kFBuf);
+        F_BULK(bulk_s2g(a.dz16t + static_cast<size_t>(tile) * kFBuf, bZ, kFBuf));
         bulk_commit();
       }
       NVP_TL(elected && it == 3, 13);
@@ -619,7 +757,8 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
 
 // Weight stream of the fused kernel, one 16 KiB panel per ring stage, in the MMA warp's consumption order:
 //   F1  [W1z 0][W1z 1][W1h 0][Ws1 0][W1h 1][Ws1 1]        F2  [W2z 0][W2z 1][W2h 0][Ws2 0][W2h 1][Ws2 1]
-//   G2  [Ws2^T 0][W2h^T 0][W2z^T 0][Ws2^T 1][W2h^T 1][W2z^T 1]   G1  the same for layer 1
+//   G2  [Ws2^T 0][W2h^T 0][Ws2^T 1][W2h^T 1] (da1, dh1: the next phase waits for them) [W2z^T 0][W2z^T 1] (dz)
+//   G1  the same for layer 1
 //   G0 / next F0  [W0z^T 0][W0z 0][W0z 1][W0z^T 1]
 // Forward panels: 64 K columns of a [128 out x K] matrix; backward panels: 64 output features (K) of the transposed
 // [N = input features, 128] matrix.
@@ -628,9 +767,15 @@ int pack_fused_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, cud
   PackArgs a{};
   a.dst = dst;
   uint32_t off = 0;
+  // forward latent panels carry the modulator bias in the latent's two constant-1 columns Z, Z+1 (hi + lo fp16 parts)
   auto fwd_z = [&](int i, int q) {
     if (i == 0) add_panel(a, p->mod_w[0], m.Z, 0, 0, 64 * q, H, m.Z - 64 * q, H, off);
     else add_panel(a, p->mod_w[i], H + m.Z, 0, 0, H + 64 * q, H, m.Z - 64 * q, H, off);
+    PackPanel& pp = a.p[a.n - 1];
+    pp.bias = p->mod_b[i];
+    const int hi = m.Z - 64 * q, lo = m.Z + 1 - 64 * q;
+    pp.bias_hi_c = (hi >= 0 && hi < 64) ? hi : -1;
+    pp.bias_lo_c = (lo >= 0 && lo < 64) ? lo : -1;
   };
   auto fwd_h = [&](int i, int q) { add_panel(a, p->mod_w[i], H + m.Z, 0, 0, 64 * q, H, 64, H, off); };
   auto fwd_s = [&](int i, int q) { add_panel(a, p->siren_w[i], H, 0, 0, 64 * q, H, 64, H, off); };
@@ -644,8 +789,10 @@ int pack_fused_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, cud
     fwd_z(i, 0); fwd_z(i, 1);
     for (int q = 0; q < 2; ++q) { fwd_h(i, q); fwd_s(i, q); }
   }
-  for (int i = 2; i >= 1; --i)
-    for (int q = 0; q < 2; ++q) { bwd_s(i, q); bwd_h(i, q); bwd_z(i, q); }
+  for (int i = 2; i >= 1; --i) {
+    for (int q = 0; q < 2; ++q) { bwd_s(i, q); bwd_h(i, q); }
+    bwd_z(i, 0); bwd_z(i, 1);
+  }
   bwd_z(0, 0); fwd_z(0, 0); fwd_z(0, 1); bwd_z(0, 1);
   ScopedKernelTimer timer(K_PACK, st);
   pack_weights_kernel<<<a.n, 256, 0, st>>>(a);

@@ -13,6 +13,7 @@
 // shared memory, so all global->shared traffic is plain bulk TMA and the same stored activation tile
 // serves the forward, dgrad (K-major) and wgrad (MN-major) GEMMs.
 #include <algorithm>
+#include <atomic>
 #include <initializer_list>
 
 #include <stdlib.h>
@@ -53,6 +54,10 @@ struct PackPanel {
   int rvalid, cvalid;  // elements outside are zero
   int rows;        // panel rows (128 or ZP)
   uint32_t dst_off;
+  // fused kernel: a bias folded into the GEMM through the latent's two constant-1 columns.  Panel column bias_hi_c gets
+  // fp16(b[r]), column bias_lo_c gets fp16(b[r] - fp16(b[r])) (-1: not in this panel); the two products sum to b in fp32.
+  const float* bias;
+  int bias_hi_c, bias_lo_c;
 };
 struct PackArgs {
   PackPanel p[kMaxPack];
@@ -70,6 +75,11 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
     if (r < pp.rvalid && c < pp.cvalid)
       v = pp.transpose ? __ldg(pp.src + static_cast<size_t>(pp.c0 + c) * pp.ld + pp.r0 + r)
                        : __ldg(pp.src + static_cast<size_t>(pp.r0 + r) * pp.ld + pp.c0 + c);
+    if (pp.bias != nullptr && r < pp.rvalid) {
+      const float b = __ldg(pp.bias + pp.r0 + r);
+      if (c == pp.bias_hi_c) v = b;
+      else if (c == pp.bias_lo_c) v = b - __half2float(__float2half_rn(b));
+    }
     *reinterpret_cast<__half*>(dst + panel_offset(r, c)) = __float2half_rn(v);
   }
 }
@@ -95,6 +105,7 @@ void add_panel(PackArgs& a, const float* src, int ld, int transpose, int r0, int
   p.src = src; p.ld = ld; p.transpose = transpose; p.r0 = r0; p.c0 = c0;
   p.rvalid = std::max(0, std::min(rvalid, rows)); p.cvalid = std::max(0, std::min(cvalid, 64));
   p.rows = rows; p.dst_off = off;
+  p.bias = nullptr; p.bias_hi_c = p.bias_lo_c = -1;
   off += static_cast<uint32_t>(rows) * 128u;
 }
 
@@ -1087,6 +1098,7 @@ int pack_backward_panels(const nvp_desc* d, const nvp_params* p, PackArgs& a, ui
 
 struct TcWorkspace {
   uint8_t* wpk_fused;
+  uint8_t* fconsts;
   uint8_t* wpk_fwd;
   uint8_t* wpk_bwd;
   uint8_t* z16t;
@@ -1111,6 +1123,7 @@ TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
   w.wpk_fwd = take(m.fwd_bytes);
   w.wpk_bwd = take(static_cast<size_t>(8) * kPanelBytes + static_cast<size_t>(6) * m.ZP * 128);
   w.wpk_fused = take(static_cast<size_t>(kFPanelsPerTile) * kPanelBytes);
+  w.fconsts = take(sizeof(FusedConsts));
   w.z16t = take(static_cast<size_t>(tiles) * m.KZ * kPanelBytes);
   w.rgb = reinterpret_cast<float*>(take(static_cast<size_t>(tiles) * kTile * 3 * sizeof(float)));
   {
@@ -1244,7 +1257,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   // The fused forward+backward kernel covers latents of up to 127 columns (two 64-wide panels: config S); wider ones
   // (config L) take the three-kernel path.  NVP_MLP_FUSED=0 forces the latter (A/B measurements).
   static const bool fused_enabled = [] { const char* v = getenv("NVP_MLP_FUSED"); return !(v && atoi(v) == 0); }();
-  const bool fused = fused_enabled && m.KZ == 2;
+  const bool fused = fused_enabled && m.KZ == 2 && m.Z + 2 <= 128;   // two constant-1 latent columns must fit
   float* rgb = out_rgb ? out_rgb : w.rgb;
   BwdArgs b{};
 
@@ -1252,10 +1265,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   if (fused) { if ((rc = pack_fused_weights(d, p, w.wpk_fused, st))) return rc; }
   else if ((rc = pack_forward_weights(d, p, w.wpk_fwd, &b, st, w.wpk_bwd))) return rc;
 
-  // 3. positional features.  Rows past n of the last tile are never written by the gather: clear them so that the
-  //    dense layers see finite values there (their gradients are zero: dL/drgb = 0 for those rows).
-  if (n % kTile != 0)
-    NVP_CUDA(cudaMemsetAsync(w.z16t + static_cast<size_t>(n_tiles - 1) * m.KZ * kPanelBytes, 0, static_cast<size_t>(m.KZ) * kPanelBytes, st));
+  // 3. positional features (the gather zero-fills the rows past n of the last tile)
   if (w.binws) {
     if ((rc = launch_grid_bin(d, tab, coords, n, m.KZ, w.binws, st))) return rc;
     if ((rc = launch_grid_gather_binned(d, tab, p, coords, n, w.z16t, m.KZ, w.binws, st))) return rc;
@@ -1266,9 +1276,21 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
   if (fused) {
     // 4+5. fused forward + loss + backward
     FusedArgs f{};
-    f.wpk = w.wpk_fused; f.z16t = w.z16t; f.tau = tsteps;
-    for (int i = 0; i < 3; ++i) { f.mod_b[i] = p->mod_b[i]; f.siren_b[i] = p->siren_b[i]; }
-    f.siren_w0 = p->siren_w[0]; f.last_w = p->last_w; f.last_b = p->last_b; f.w0 = d->w0_first;
+    f.wpk = w.wpk_fused; f.z16t = w.z16t; f.tau = tsteps; f.w0 = d->w0_first;
+    {
+      // epilogue constants -> a slot of constant memory (stream-ordered device-to-device copy)
+      static std::atomic<unsigned> next_slot{0};
+      f.cslot = static_cast<int>(next_slot.fetch_add(1) % kFConstSlots);
+      FusedConsts* staged = reinterpret_cast<FusedConsts*>(w.fconsts);
+      f.consts = reinterpret_cast<const float*>(staged);
+      fused_consts_kernel<<<1, H, 0, st>>>(staged, p->siren_b[0], p->siren_b[1], p->siren_b[2], p->siren_w[0], p->last_w, p->last_b,
+                                           d->w0_first);
+      NVP_LAUNCH_CHECK();
+#if NVP_FCONST == 1
+      NVP_CUDA(cudaMemcpyToSymbolAsync(g_fused_consts, staged, sizeof(FusedConsts), static_cast<size_t>(f.cslot) * sizeof(FusedConsts),
+                                       cudaMemcpyDeviceToDevice, st));
+#endif
+    }
     f.gt = gt_u8; f.dout = dout; f.gscale = w.gscale; f.rgb_out = out_rgb;
     f.stash = w.stash; f.dpre = w.dpre; f.dz16t = w.dz16t; f.loss_sum = loss_sum;
     f.g_last_w = g->last_w; f.g_last_b = g->last_b; f.g_siren_b1 = g->siren_b[1]; f.g_siren_b2 = g->siren_b[2];
