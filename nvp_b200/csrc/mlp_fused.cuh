@@ -44,8 +44,10 @@ enum { FS_H0 = 0, FS_A0, FS_H1, FS_A1, FS_COUNT };   // stash slots the weight-g
 enum {
   FB_WFULL = 0, FB_WEMPTY = 3, FB_ZFULL = 6,
   FB_AF_P0 = 7, FB_AF_P1, FB_AF_P2, FB_AF_P4, FB_AF_P5, FB_AF_P6,
-  FB_PD_P0 = 13, FB_PD_P1 = 15, FB_PD_P3 = 17, FB_PD_P4 = 19, FB_PD_P5 = 21,
-  FB_TF_P0 = 23, FB_TF_P4, FB_G2_DONE, FB_DM2_STORED, FB_A2_READY, FB_RD_A2, FB_RD_DSP2, FB_RD_DSP1, FB_RD_DSP0, FB_COUNT
+  FB_PD_P0 = 13, FB_PD_P1 = 15, FB_PD_P3 = 17, FB_PD_P4 = 19, FB_PD_P5 = 21, FB_PD_P6 = 23,   // panel done (one arrival per epilogue warp)
+  FB_TF_P0 = 24, FB_TF_P4, FB_G2_DONE, FB_A2_READY, FB_RD_A2, FB_RD_DSP2, FB_RD_DSP1, FB_RD_DSP0,
+  FB_SR_P0, FB_SR_P1, FB_SR_P3, FB_SR_P4, FB_SR_P5, FB_SR_P6,   // the bulk stores of that phase's tiles have left shared memory
+  FB_COUNT
 };
 
 struct FusedArgs {
@@ -132,7 +134,7 @@ __host__ __device__ constexpr FusedSmem fused_smem_layout() {
   s.bufs = o; o += 5u * kFBuf;
   s.ring = o; o += kFStages * kPanelBytes;
   s.consts = o; o += (sizeof(FusedConsts) + 15) / 16 * 16;
-  s.rowdata = o; o += kTile * 16;        // per row: drgb0..2 (times gs), tau
+  s.rowdata = o; o += kTile * 16;        // per row: drgb0..2 (times gs) and tau, each as an fp16 pair
   s.xch = o; o += kFSub * kTile * 16;    // partial rgb of the column slices
   s.bars = o; o += 64 * 8;
   s.tmem = o; o += 16;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(FusedConsts) / 4); i += kFThreads)
     reinterpret_cast<float*>(smem + L.consts)[i] = __ldg(a.consts + i);
 #endif
-  float4* s_row = reinterpret_cast<float4*>(smem + L.rowdata);
+  uint4* s_row = reinterpret_cast<uint4*>(smem + L.rowdata);   // per row: (d0,d0) (d1,d1) (d2,d2) (tau,tau) as fp16 pairs
   float4* s_xch = reinterpret_cast<float4*>(smem + L.xch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem);
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
   if (tid == 0) {
     for (int i = 0; i < FB_COUNT; ++i) {
       uint32_t cnt = 1;
-      if (i == FB_TF_P0 || i == FB_TF_P4) cnt = kFEpiWarps;
+      if (i == FB_TF_P0 || i == FB_TF_P4 || (i >= FB_PD_P0 && i <= FB_PD_P6)) cnt = kFEpiWarps;
       if (i == FB_A2_READY) cnt = kTile;
       if (i >= FB_RD_A2 && i <= FB_RD_DSP0) cnt = 2;
       mbar_init(&bars[i], cnt);
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
           if (i == 20 && has_next) {
             // the A1 buffer (dm2) has been read by G2 and by its bulk store: load the next tile's latent into it
             mbar_wait(&bars[FB_G2_DONE], it & 1);
-            mbar_wait(&bars[FB_DM2_STORED], it & 1);
+            mbar_wait(&bars[FB_SR_P3], it & 1);
             mbar_arrive_expect_tx(&bars[FB_ZFULL], kFBuf);
             bulk_g2s(buf_a1(it), a.z16t + static_cast<size_t>(tile_of(it + 1)) * kFBuf, kFBuf, &bars[FB_ZFULL]);
           }
@@ -282,6 +284,16 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         ++g;
       };
       auto wait_pd = [&](int bar, uint32_t par) { mbar_wait(&bars[bar], par); tcgen05_fence_after(); };
+      // This thread also hands finished operand tiles to the TMA for the weight-gradient kernel: it is the one that
+      // observes every panel-done barrier anyway, and issuing a cp.async.bulk takes ~150 cycles that the epilogue warps
+      // would otherwise spend on their critical path.  Stores are issued after the MMAs of the same panel.
+      auto store2 = [&](uint8_t* dst0, const uint8_t* src0, uint8_t* dst1, const uint8_t* src1, uint32_t bytes) {
+        F_BULK(bulk_s2g(dst0, src0, bytes));
+        F_BULK(if (dst1) bulk_s2g(dst1, src1, bytes));
+        bulk_commit();
+      };
+      // all bulk stores issued so far have left shared memory: the tiles of phase `sr_bar` may be overwritten
+      auto stores_read = [&](int sr_bar) { bulk_wait_read0(); mbar_arrive(&bars[sr_bar]); };
       // F0 of the first tile
       wait_pd(FB_ZFULL, 0);
       gemm(buf_z(0), S1, false); gemm(buf_z(0) + kPanelBytes, S1, true);
@@ -292,6 +304,11 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         uint8_t* const bZ = buf_z(it);
         uint8_t* const bA1 = buf_a1(it);
         const uint32_t P = kPanelBytes;
+        const int tile = tile_of(it);
+        uint8_t* const st_base = a.stash + static_cast<size_t>(tile) * FS_COUNT * kFBuf;
+        uint8_t* const dp_base = a.dpre + static_cast<size_t>(tile) * DP_COUNT * kFBuf;
+        auto st_dst = [&](int slot, int p) { return st_base + static_cast<size_t>(slot) * kFBuf + static_cast<size_t>(p) * kPanelBytes; };
+        auto dp_dst = [&](int slot, int p) { return dp_base + static_cast<size_t>(slot) * kFBuf + static_cast<size_t>(p) * kPanelBytes; };
 #ifdef NVP_TIMELINE
         if (it == 3) ring_wait = 0;
 #endif
@@ -300,24 +317,31 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         gemm(bZ, S0, false); gemm(bZ + P, S0, true);
         wait_pd(FB_PD_P0 + 0, par); wait_pd(FB_TF_P0, par);
         gemm(bH0, S0, true); gemm(bA0, S1, false);
+        store2(st_dst(FS_H0, 0), bH0, st_dst(FS_A0, 0), bA0, P);
         wait_pd(FB_PD_P0 + 1, par);
         NVP_TL(it == 3, 65);
         gemm(bH0 + P, S0, true); gemm(bA0 + P, S1, true);
         umma_commit(&bars[FB_AF_P1]);
+        store2(st_dst(FS_H0, 1), bH0 + P, st_dst(FS_A0, 1), bA0 + P, P);
         NVP_TL(it == 3, 80);
         // ---- F2: m2 -> S2, sp2 -> S3 ----
         gemm(bZ, S2, false); gemm(bZ + P, S2, true);
+        stores_read(FB_SR_P0);
         wait_pd(FB_PD_P1 + 0, par);
         gemm(bH1, S2, true); gemm(bA1, S3, false);
+        store2(st_dst(FS_H1, 0), bH1, st_dst(FS_A1, 0), bA1, P);
         wait_pd(FB_PD_P1 + 1, par);
         NVP_TL(it == 3, 66);
         gemm(bH1 + P, S2, true); gemm(bA1 + P, S3, true);
         umma_commit(&bars[FB_AF_P2]);
+        store2(st_dst(FS_H1, 1), bH1 + P, st_dst(FS_A1, 1), bA1 + P, P);
+        stores_read(FB_SR_P1);   // a1 / h1 are on their way: P3 may write dsp2 / dm2 over a0 / a1 (idle time: G2 waits for P2 + P3)
         NVP_TL(it == 3, 81);
         // ---- G2: da1 = dsp2 Ws2 -> S0, dh1 = dm2 W2h -> S2 (dsp2 in A0, dm2 in A1); then dz = dm2 W2z -> S3 ----
         wait_pd(FB_PD_P3 + 0, par);
         NVP_TL(it == 3, 67);
         gemm(bA0, S0, false); gemm(bA1, S2, false);
+        store2(dp_dst(DP_S2, 0), bA0, dp_dst(DP_M2, 0), bA1, P);
         wait_pd(FB_PD_P3 + 1, par);
         NVP_TL(it == 3, 68);
         gemm(bA0 + P, S0, true); gemm(bA1 + P, S2, true);
@@ -325,21 +349,27 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 82);
         gemm(bA1, S3, false); gemm(bA1 + P, S3, true);
         umma_commit(&bars[FB_G2_DONE]);
+        store2(dp_dst(DP_S2, 1), bA0 + P, dp_dst(DP_M2, 1), bA1 + P, P);
+        stores_read(FB_SR_P3);   // the producer may load the next latent tile over dm2; P5 may write dsp0 over dsp2
         // ---- G1: da0 = dsp1 Ws1 -> S0, dh0 = dm1 W1h -> S2 (dsp1 in Z, dm1 in H1); then dz += dm1 W1z ----
         // S0 / S2 are still read by P4 until it has loaded its last panel from TMEM (FB_TF_P4)
         wait_pd(FB_PD_P4 + 0, par); wait_pd(FB_TF_P4, par);
         NVP_TL(it == 3, 69);
         gemm(bZ, S0, false); gemm(bH1, S2, false);
+        store2(dp_dst(DP_S1, 0), bZ, dp_dst(DP_M1, 0), bH1, P);
         wait_pd(FB_PD_P4 + 1, par);
         NVP_TL(it == 3, 70);
         gemm(bZ + P, S0, true); gemm(bH1 + P, S2, true);
         umma_commit(&bars[FB_AF_P5]);
         NVP_TL(it == 3, 83);
         gemm(bH1, S3, true); gemm(bH1 + P, S3, true);
+        store2(dp_dst(DP_S1, 1), bZ + P, dp_dst(DP_M1, 1), bH1 + P, P);
+        stores_read(FB_SR_P4);   // P6 may stage dz over dsp1
         // ---- G0 (dz += dm0 W0z, dm0 in H0) around F0 of the next tile (m0 -> S1, free since FB_TF_P4) ----
         wait_pd(FB_PD_P5 + 0, par);
         NVP_TL(it == 3, 71);
         gemm(bH0, S3, true);
+        store2(dp_dst(DP_M0, 0), bH0, nullptr, nullptr, P);
         if (has_next) {
           wait_pd(FB_ZFULL, par ^ 1);
           gemm(bA1, S1, false); gemm(bA1 + P, S1, true);
@@ -349,14 +379,22 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 72);
         gemm(bH0 + P, S3, true);
         umma_commit(&bars[FB_AF_P6]);
+        store2(dp_dst(DP_M0, 1), bH0 + P, nullptr, nullptr, P);
+        stores_read(FB_SR_P5);   // the next tile's P0 may write h0 over dm0
+        // dz, staged in Z by P6
+        mbar_wait(&bars[FB_PD_P6], par);
+        store2(a.dz16t + static_cast<size_t>(tile) * kFBuf, bZ, nullptr, nullptr, kFBuf);
+        stores_read(FB_SR_P6);   // the next tile's P1 may write a1 there
 #ifdef NVP_TIMELINE
         if (it == 3 && blockIdx.x == 0) g_timeline[90] = static_cast<unsigned long long>(ring_wait);
 #endif
       }
+      bulk_wait_all0();
     }
   } else if (warp < 4) {
     // ================= reducers: column sums over the samples of a tile =================
-    // Warp w owns the 64 columns of panel w of every operand tile; lane l owns columns 2l, 2l+1 of that panel.
+    // Warp w owns the 64 columns of panel w of every operand tile; lane l owns columns 2l, 2l+1 of that panel.  Groups of
+    // 8 rows are summed as packed fp16 pairs (the operands are fp16 already), the group sums are accumulated in fp32.
     const int w = warp - 2;
     const uint32_t poff = static_cast<uint32_t>(w) * kPanelBytes;
     const uint32_t lane_off = static_cast<uint32_t>(lane & 3) * 4u;
@@ -364,49 +402,66 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
     float wl0a = 0.f, wl0b = 0.f, wl1a = 0.f, wl1b = 0.f, wl2a = 0.f, wl2b = 0.f;
     float b2a = 0.f, b2b = 0.f, b1a = 0.f, b1b = 0.f, b0a = 0.f, b0b = 0.f, w0a = 0.f, w0b = 0.f;
     auto ldx = [&](const uint8_t* tile, int r) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + poff + static_cast<uint32_t>(r) * 128u +
-                                                            ((lane_chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4) + lane_off);
-      return unpack_half2(v);
+      return *reinterpret_cast<const __half2*>(tile + poff + static_cast<uint32_t>(r) * 128u +
+                                               ((lane_chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4) + lane_off);
     };
     auto arrive = [&](int bar) { __syncwarp(); if (lane == 0) mbar_arrive(&bars[bar]); };
+    auto colsum = [&](const uint8_t* tile, float& sa, float& sb) {
+#if !(NVP_ABL & 16)
+#pragma unroll 2
+      for (int r0 = 0; r0 < kTile; r0 += 8) {
+        __half2 acc = ldx(tile, r0);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc = __hadd2(acc, ldx(tile, r0 + j));
+        const float2 f = __half22float2(acc);
+        sa += f.x; sb += f.y;
+      }
+#endif
+    };
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const uint8_t* const bZ = buf_z(it);
       mbar_wait(&bars[FB_A2_READY], par);   // a2 (both panels) and the per-row drgb / tau are in place
 #if !(NVP_ABL & 16)
-#pragma unroll 4
-      for (int r = 0; r < kTile; ++r) {
-        const float2 x = ldx(bZ, r);
-        const float4 d = s_row[r];
-        wl0a = fmaf(d.x, x.x, wl0a); wl0b = fmaf(d.x, x.y, wl0b);
-        wl1a = fmaf(d.y, x.x, wl1a); wl1b = fmaf(d.y, x.y, wl1b);
-        wl2a = fmaf(d.z, x.x, wl2a); wl2b = fmaf(d.z, x.y, wl2b);
+#pragma unroll 2
+      for (int r0 = 0; r0 < kTile; r0 += 8) {
+        __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half2 x = ldx(bZ, r0 + j);
+          const uint4 d = s_row[r0 + j];   // (drgb0, drgb0) (drgb1, drgb1) (drgb2, drgb2) (tau, tau) as fp16 pairs
+          a0 = __hfma2(x, *reinterpret_cast<const __half2*>(&d.x), a0);
+          a1 = __hfma2(x, *reinterpret_cast<const __half2*>(&d.y), a1);
+          a2 = __hfma2(x, *reinterpret_cast<const __half2*>(&d.z), a2);
+        }
+        const float2 f0 = __half22float2(a0), f1 = __half22float2(a1), f2 = __half22float2(a2);
+        wl0a += f0.x; wl0b += f0.y; wl1a += f1.x; wl1b += f1.y; wl2a += f2.x; wl2b += f2.y;
       }
 #endif
       arrive(FB_RD_A2);
       NVP_TL(w == 0 && lane == 0 && it == 3, 48);
       mbar_wait(&bars[FB_PD_P3 + w], par);
-#if !(NVP_ABL & 16)
-#pragma unroll 4
-      for (int r = 0; r < kTile; ++r) { const float2 x = ldx(bA0, r); b2a += x.x; b2b += x.y; }
-#endif
+      colsum(bA0, b2a, b2b);
       arrive(FB_RD_DSP2);
       NVP_TL(w == 0 && lane == 0 && it == 3, 49);
       mbar_wait(&bars[FB_PD_P4 + w], par);
-#if !(NVP_ABL & 16)
-#pragma unroll 4
-      for (int r = 0; r < kTile; ++r) { const float2 x = ldx(bZ, r); b1a += x.x; b1b += x.y; }
-#endif
+      colsum(bZ, b1a, b1b);
       arrive(FB_RD_DSP1);
       NVP_TL(w == 0 && lane == 0 && it == 3, 50);
       mbar_wait(&bars[FB_PD_P5 + w], par);
 #if !(NVP_ABL & 16)
-#pragma unroll 4
-      for (int r = 0; r < kTile; ++r) {
-        const float2 x = ldx(bA0, r);
-        const float t = s_row[r].w;
-        b0a += x.x; b0b += x.y;
-        w0a = fmaf(t, x.x, w0a); w0b = fmaf(t, x.y, w0b);
+#pragma unroll 2
+      for (int r0 = 0; r0 < kTile; r0 += 8) {
+        __half2 a0 = __float2half2_rn(0.f), a1 = a0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half2 x = ldx(bA0, r0 + j);
+          const uint32_t t = s_row[r0 + j].w;
+          a0 = __hadd2(a0, x);
+          a1 = __hfma2(x, *reinterpret_cast<const __half2*>(&t), a1);
+        }
+        const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
+        b0a += f0.x; b0b += f0.y; w0a += f1.x; w0b += f1.y;
       }
 #endif
       arrive(FB_RD_DSP0);
@@ -438,20 +493,17 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
     const float gs = __ldg(a.gscale), inv_gs = __ldg(a.gscale + 1), loss_mult = __ldg(a.gscale + 2);
     float loss_acc = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f;
 
-    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kFEpiThreads) : "memory"); };
-    // end of a panel: operand tiles visible to the async proxy, then one thread releases the MMA warp and hands the
-    // panel(s) to the TMA for the weight-gradient kernel
-    auto panel_end = [&](int pd_bar, uint8_t* dst0, const uint8_t* src0, uint8_t* dst1, const uint8_t* src1) {
+    // rows are shared by the kFSub warps of a TMEM lane quarter: their barrier (rgb exchange)
+    auto quarter_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + quarter), "n"(kFSub * 32) : "memory"); };
+    // end of a panel: my operand chunks are visible to the async proxy (UMMA reads, bulk stores); one arrival per warp.
+    // There is no barrier among the epilogue warps: each runs on into its next panel.
+    auto panel_end = [&](int pd_bar) {
       fence_proxy_async_smem();
       tcgen05_fence_before();
-      epi_sync();
-      if (elected) {
-        mbar_arrive(&bars[pd_bar]);
-        F_BULK(if (dst0) bulk_s2g(dst0, src0, kPanelBytes));
-        F_BULK(if (dst1) bulk_s2g(dst1, src1, kPanelBytes));
-        bulk_commit();
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[pd_bar]);
     };
+    auto wait_bar = [&](int bar, uint32_t par) { mbar_wait(&bars[bar], par); };
     auto tmem_release = [&](int bar) { tcgen05_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&bars[bar]); };
     auto wait_acc = [&](int af_bar, uint32_t par) { mbar_wait(&bars[af_bar], par); tcgen05_fence_after(); };
 
@@ -467,10 +519,6 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       const bool valid = s < a.n;
       uint8_t* const bZ = buf_z(it);
       uint8_t* const bA1 = buf_a1(it);
-      uint8_t* const st_base = a.stash + static_cast<size_t>(tile) * FS_COUNT * kFBuf;
-      uint8_t* const dp_base = a.dpre + static_cast<size_t>(tile) * DP_COUNT * kFBuf;
-      auto st_dst = [&](int slot, int p) { return st_base + static_cast<size_t>(slot) * kFBuf + static_cast<size_t>(p) * kPanelBytes; };
-      auto dp_dst = [&](int slot, int p) { return dp_base + static_cast<size_t>(slot) * kFBuf + static_cast<size_t>(p) * kPanelBytes; };
       // ground truth of my row, fetched a few phases before it is needed
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
       if (valid && a.dout == nullptr) {
@@ -484,11 +532,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       wait_acc(FB_AF_P0, par);
       NVP_TL(elected && it == 3, 0);
       NVP_TL(elected && it == 4, 14);
-      if (elected) {
-        bulk_wait_read<1>();   // all earlier bulk stores but the newest (dz, from the Z buffer) have left shared memory
-        if (it > 0) mbar_wait(&bars[FB_RD_DSP0], par ^ 1);
-      }
-      epi_sync();
+      if (it > 0) { wait_bar(FB_SR_P5, par ^ 1); wait_bar(FB_RD_DSP0, par ^ 1); }   // dm0 stored; reducers done with dsp0
       NVP_TL(elected && it == 3, 16);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
@@ -505,7 +549,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         }
         F_STORE(store_rown<C>(bH0 + p * kPanelBytes, r, pc, hv));
         F_STORE(store_rown<C>(bA0 + p * kPanelBytes, r, pc, av));
-        panel_end(FB_PD_P0 + p, st_dst(FS_H0, p), bH0 + p * kPanelBytes, st_dst(FS_A0, p), bA0 + p * kPanelBytes);
+        panel_end(FB_PD_P0 + p);
       }
       NVP_TL(elected && it == 3, 1);
 
@@ -513,8 +557,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       // writes H1 (dm1 of the previous tile) and A1 (= the previous tile's Z buffer: its dz store must have left)
       wait_acc(FB_AF_P1, par);
       NVP_TL(elected && it == 3, 2);
-      if (elected) bulk_wait_read<2>();
-      epi_sync();
+      if (it > 0) { wait_bar(FB_SR_P4, par ^ 1); wait_bar(FB_SR_P6, par ^ 1); wait_bar(FB_RD_DSP1, par ^ 1); }   // dm1, dz stored; dsp1 reduced
       NVP_TL(elected && it == 3, 17);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
@@ -531,7 +574,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         }
         F_STORE(store_rown<C>(bH1 + p * kPanelBytes, r, pc, hv));
         F_STORE(store_rown<C>(bA1 + p * kPanelBytes, r, pc, av));
-        panel_end(FB_PD_P1 + p, st_dst(FS_H1, p), bH1 + p * kPanelBytes, st_dst(FS_A1, p), bA1 + p * kPanelBytes);
+        panel_end(FB_PD_P1 + p);
       }
       NVP_TL(elected && it == 3, 3);
 
@@ -573,8 +616,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       }
       // rgb of my row = the sum over the column slices
       s_xch[sub * kTile + r] = make_float4(rgb0, rgb1, rgb2, 0.f);
-      if (elected) bulk_wait_read<0>();   // the a0 / a1 stores have left A0 / A1 long ago: P3 writes there
-      epi_sync();
+      quarter_sync();
 #pragma unroll
       for (int q = 1; q < kFSub; ++q) {
         const float4 o = s_xch[((sub + q) % kFSub) * kTile + r];
@@ -594,12 +636,13 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       }
       if (sub == 0) {
         gb0 += d0; gb1 += d1; gb2 += d2;
-        s_row[r] = make_float4(d0, d1, d2, tau);
+        s_row[r] = make_uint4(pack_half2(d0, d0), pack_half2(d1, d1), pack_half2(d2, d2), pack_half2(tau, tau));
         mbar_arrive(&bars[FB_A2_READY]);    // releases my a2 / row data (and, through the barrier above, everybody's a2)
       }
       NVP_TL(elected && it == 3, 5);
 
       // ---------------- P3: da2 = drgb Wl ; dsp2 = da2 u -> A0 ; dm2 = da2 v -> A1 ----------------
+      wait_bar(FB_SR_P0, par); wait_bar(FB_SR_P1, par);   // the a0 / a1 stores have left A0 / A1
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int col = p * 64 + pc;
@@ -614,19 +657,14 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         }
         F_STORE(store_packed<C>(bA0 + p * kPanelBytes, r, pc, o1));
         F_STORE(store_packed<C>(bA1 + p * kPanelBytes, r, pc, o2));
-        panel_end(FB_PD_P3 + p, dp_dst(DP_S2, p), bA0 + p * kPanelBytes, dp_dst(DP_M2, p), bA1 + p * kPanelBytes);
+        panel_end(FB_PD_P3 + p);
       }
       NVP_TL(elected && it == 3, 6);
 
       // ---------------- P4: dsp1 = da1 h1 cos1 (Z, over a2) ; dm1 = (dh1 + da1 sin1) lrelu'(h1) (H1, in place) ----------------
       wait_acc(FB_AF_P4, par);
       NVP_TL(elected && it == 3, 8);
-      if (elected) {
-        bulk_wait_read<0>();                      // dsp2 / dm2 have left A0 / A1 ...
-        mbar_arrive(&bars[FB_DM2_STORED]);        // ... so the producer may load the next latent tile over dm2
-        mbar_wait(&bars[FB_RD_A2], par);          // the reducers are done with a2
-      }
-      epi_sync();
+      wait_bar(FB_RD_A2, par);   // the reducers are done with a2 (Z); h1's store left H1 before P3
       NVP_TL(elected && it == 3, 18);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
@@ -656,18 +694,14 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         }
         F_STORE(store_packed<C>(bZ + p * kPanelBytes, r, pc, o1));
         F_STORE(store_packed<C>(bH1 + p * kPanelBytes, r, pc, o2));
-        panel_end(FB_PD_P4 + p, dp_dst(DP_S1, p), bZ + p * kPanelBytes, dp_dst(DP_M1, p), bH1 + p * kPanelBytes);
+        panel_end(FB_PD_P4 + p);
       }
       NVP_TL(elected && it == 3, 9);
 
       // ---------------- P5: dsp0 = da0 h0 cos0 (A0, over dsp2) ; dm0 = (dh0 + da0 sin0) lrelu'(h0) (H0, in place) ----------------
       wait_acc(FB_AF_P5, par);
       NVP_TL(elected && it == 3, 10);
-      if (elected) {
-        bulk_wait_read<2>();                      // everything but P4's two groups (dsp1 / dm1, in Z / H1)
-        mbar_wait(&bars[FB_RD_DSP2], par);        // the reducers are done with dsp2
-      }
-      epi_sync();
+      wait_bar(FB_SR_P3, par); wait_bar(FB_RD_DSP2, par);   // dsp2 stored and reduced (A0); h0's store left H0 before P3
       NVP_TL(elected && it == 3, 19);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
@@ -695,7 +729,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         }
         F_STORE(store_packed<C>(bA0 + p * kPanelBytes, r, pc, o1));
         F_STORE(store_packed<C>(bH0 + p * kPanelBytes, r, pc, o2));
-        panel_end(FB_PD_P5 + p, dp_dst(DP_M0, p), bH0 + p * kPanelBytes, nullptr, nullptr);
+        panel_end(FB_PD_P5 + p);
       }
       NVP_TL(elected && it == 3, 11);
       // tau of the next tile's row (consumed at its P0, needed by the reducers until this tile's dsp0 sum is done:
@@ -708,11 +742,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       // ---------------- P6: dz -> fp16 tile staged in Z (over dsp1) -> HBM ----------------
       wait_acc(FB_AF_P6, par);
       NVP_TL(elected && it == 3, 12);
-      if (elected) {
-        bulk_wait_read<2>();                      // everything but P5's two groups (dm0, in H0)
-        mbar_wait(&bars[FB_RD_DSP1], par);        // the reducers are done with dsp1
-      }
-      epi_sync();
+      wait_bar(FB_SR_P4, par); wait_bar(FB_RD_DSP1, par);   // dsp1 stored and reduced (Z)
       NVP_TL(elected && it == 3, 20);
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
@@ -724,16 +754,9 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         for (int i = 0; i < C; ++i) f[i] = __uint_as_float(v[i]);
         F_STORE(store_rown<C>(bZ + q * kPanelBytes, r, pc, f));
       }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      epi_sync();
-      if (elected) {
-        F_BULK(bulk_s2g(a.dz16t + static_cast<size_t>(tile) * kFBuf, bZ, kFBuf));
-        bulk_commit();
-      }
+      panel_end(FB_PD_P6);   // the MMA thread stores the tile
       NVP_TL(elected && it == 3, 13);
     }
-    if (elected) bulk_wait_all0();
     if (my_tiles > 0 && sub == 0) {
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) {

@@ -18,26 +18,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void ring(const uint8_t* src, uint32_t src_bytes, uint32_t stage_bytes, int nstage, int n_loads, long long* cycles) {
+// nprod producer threads (lane 0 of warps 0..nprod-1): producer q issues the loads g with g % nprod == q.
+__global__ void ring(const uint8_t* src, uint32_t src_bytes, uint32_t stage_bytes, int nstage, int n_loads, long long* cycles, int nprod) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full[16], empty[16];
+  __shared__ uint64_t full[32], empty[32];
   if (threadIdx.x == 0) {
     for (int i = 0; i < nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const long long t0 = clock64();
-  if (threadIdx.x == 0) {
-    uint32_t off = (blockIdx.x * 4096u) % src_bytes;
-    for (int g = 0; g < n_loads; ++g) {
+  const int warp = threadIdx.x >> 5;
+  if (warp < nprod && (threadIdx.x & 31) == 0) {
+    for (int g = warp; g < n_loads; g += nprod) {
       const int st = g % nstage, ph = (g / nstage) & 1;
+      const uint32_t off = (static_cast<uint32_t>(g) * stage_bytes) % src_bytes;
       mbar_wait(&empty[st], ph ^ 1);
       mbar_expect(&full[st], stage_bytes);
-      if (off + stage_bytes > src_bytes) off = 0;
       bulk_g2s(smem + static_cast<size_t>(st) * stage_bytes, src + off, stage_bytes, &full[st]);
-      off += stage_bytes;
     }
-  } else if (threadIdx.x == 32) {
+  } else if (threadIdx.x == 32 * nprod) {
     for (int g = 0; g < n_loads; ++g) {
       const int st = g % nstage, ph = (g / nstage) & 1;
       mbar_wait(&full[st], ph);
@@ -48,24 +48,27 @@ __global__ void ring(const uint8_t* src, uint32_t src_bytes, uint32_t stage_byte
 }
 
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
   const uint32_t src_bytes = 448 * 1024;
   uint8_t* src; long long* cyc;
   cudaMalloc(&src, src_bytes); cudaMemset(src, 1, src_bytes);
   cudaMalloc(&cyc, 148 * sizeof(long long));
   cudaFuncSetAttribute(ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int shapes[][2] = {{16384, 1}, {16384, 2}, {16384, 3}, {16384, 4}, {16384, 6}, {16384, 8}, {16384, 12},
-                           {8192, 3}, {8192, 6}, {8192, 12}, {8192, 24}, {4096, 12}, {4096, 24}, {32768, 2}, {32768, 3}, {32768, 6}};
+  const int shapes[][3] = {{16384, 1, 1}, {16384, 2, 1}, {16384, 3, 1}, {16384, 4, 1}, {16384, 6, 1}, {16384, 12, 1},
+                           {8192, 3, 1}, {8192, 6, 1}, {8192, 24, 1}, {4096, 12, 1}, {32768, 2, 1}, {32768, 3, 1}, {32768, 6, 1},
+                           {16384, 3, 2}, {16384, 4, 2}, {16384, 6, 2}, {16384, 6, 3}, {16384, 12, 4}, {8192, 6, 2}, {8192, 12, 4}, {4096, 12, 4},
+                           {32768, 4, 2}};
   for (auto& s : shapes) {
-    const uint32_t stage = s[0]; const int nst = s[1];
+    const uint32_t stage = s[0]; const int nst = s[1], nprod = s[2];
     const int n_loads = static_cast<int>(64ull * 1024 * 1024 / 148 / stage) + 1;   // ~64 MiB per launch over 148 SMs
-    for (int rep = 0; rep < 2; ++rep) ring<<<148, 64, stage * nst>>>(src, src_bytes, stage, nst, n_loads, cyc);
+    for (int rep = 0; rep < 2; ++rep) ring<<<148, 32 * nprod + 32, stage * nst>>>(src, src_bytes, stage, nst, n_loads, cyc, nprod);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
     long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
     long long mx = 0; for (long long v : h) mx = v > mx ? v : mx;
     const double per = static_cast<double>(mx) / n_loads;
-    printf("stage %6u B x %2d stages (%3u KiB in flight): %7.0f cycles per stage = %6.1f cycles per 16 KiB, %5.1f B/cycle/SM\n", stage, nst,
-           stage * nst / 1024, per, per * 16384.0 / stage, stage / per);
+    printf("stage %6u B x %2d stages, %d producer(s) (%3u KiB in flight): %7.0f cycles per stage = %6.1f cycles per 16 KiB, %5.1f B/cycle/SM\n", stage, nst,
+           nprod, stage * nst / 1024, per, per * 16384.0 / stage, stage / per);
   }
   return 0;
 }
