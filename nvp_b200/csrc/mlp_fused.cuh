@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         for (int i = 0; i < kFPanelsPerTile; ++i) {
           if ((i == 25 || i == 26) && !has_next) continue;
           issue_w(i);
-          if (i == 20 && has_next) {
+          if (i == 21 && has_next) {
             // the A1 buffer (dm2) has been read by G2 and by its bulk store: load the next tile's latent into it
             mbar_wait(&bars[FB_G2_DONE], it & 1);
             mbar_wait(&bars[FB_SR_P3], it & 1);
@@ -317,31 +317,30 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         gemm(bZ, S0, false); gemm(bZ + P, S0, true);
         wait_pd(FB_PD_P0 + 0, par); wait_pd(FB_TF_P0, par);
         gemm(bH0, S0, true); gemm(bA0, S1, false);
-        store2(st_dst(FS_H0, 0), bH0, st_dst(FS_A0, 0), bA0, P);
         wait_pd(FB_PD_P0 + 1, par);
         NVP_TL(it == 3, 65);
         gemm(bH0 + P, S0, true); gemm(bA0 + P, S1, true);
         umma_commit(&bars[FB_AF_P1]);
-        store2(st_dst(FS_H0, 1), bH0 + P, st_dst(FS_A0, 1), bA0 + P, P);
+        // (stores only after the phase's critical MMAs: a bulk store issued earlier would sit in the SM's TMA queue ahead
+        // of the weight panels those MMAs wait for)
+        store2(st_dst(FS_H0, 0), bH0, st_dst(FS_A0, 0), bA0, kFBuf);
         NVP_TL(it == 3, 80);
         // ---- F2: m2 -> S2, sp2 -> S3 ----
         gemm(bZ, S2, false); gemm(bZ + P, S2, true);
         stores_read(FB_SR_P0);
         wait_pd(FB_PD_P1 + 0, par);
         gemm(bH1, S2, true); gemm(bA1, S3, false);
-        store2(st_dst(FS_H1, 0), bH1, st_dst(FS_A1, 0), bA1, P);
         wait_pd(FB_PD_P1 + 1, par);
         NVP_TL(it == 3, 66);
         gemm(bH1 + P, S2, true); gemm(bA1 + P, S3, true);
         umma_commit(&bars[FB_AF_P2]);
-        store2(st_dst(FS_H1, 1), bH1 + P, st_dst(FS_A1, 1), bA1 + P, P);
+        store2(st_dst(FS_H1, 0), bH1, st_dst(FS_A1, 0), bA1, kFBuf);
         stores_read(FB_SR_P1);   // a1 / h1 are on their way: P3 may write dsp2 / dm2 over a0 / a1 (idle time: G2 waits for P2 + P3)
         NVP_TL(it == 3, 81);
         // ---- G2: da1 = dsp2 Ws2 -> S0, dh1 = dm2 W2h -> S2 (dsp2 in A0, dm2 in A1); then dz = dm2 W2z -> S3 ----
         wait_pd(FB_PD_P3 + 0, par);
         NVP_TL(it == 3, 67);
         gemm(bA0, S0, false); gemm(bA1, S2, false);
-        store2(dp_dst(DP_S2, 0), bA0, dp_dst(DP_M2, 0), bA1, P);
         wait_pd(FB_PD_P3 + 1, par);
         NVP_TL(it == 3, 68);
         gemm(bA0 + P, S0, true); gemm(bA1 + P, S2, true);
@@ -349,27 +348,25 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 82);
         gemm(bA1, S3, false); gemm(bA1 + P, S3, true);
         umma_commit(&bars[FB_G2_DONE]);
-        store2(dp_dst(DP_S2, 1), bA0 + P, dp_dst(DP_M2, 1), bA1 + P, P);
+        store2(dp_dst(DP_S2, 0), bA0, dp_dst(DP_M2, 0), bA1, kFBuf);
         stores_read(FB_SR_P3);   // the producer may load the next latent tile over dm2; P5 may write dsp0 over dsp2
         // ---- G1: da0 = dsp1 Ws1 -> S0, dh0 = dm1 W1h -> S2 (dsp1 in Z, dm1 in H1); then dz += dm1 W1z ----
         // S0 / S2 are still read by P4 until it has loaded its last panel from TMEM (FB_TF_P4)
         wait_pd(FB_PD_P4 + 0, par); wait_pd(FB_TF_P4, par);
         NVP_TL(it == 3, 69);
         gemm(bZ, S0, false); gemm(bH1, S2, false);
-        store2(dp_dst(DP_S1, 0), bZ, dp_dst(DP_M1, 0), bH1, P);
         wait_pd(FB_PD_P4 + 1, par);
         NVP_TL(it == 3, 70);
         gemm(bZ + P, S0, true); gemm(bH1 + P, S2, true);
         umma_commit(&bars[FB_AF_P5]);
         NVP_TL(it == 3, 83);
         gemm(bH1, S3, true); gemm(bH1 + P, S3, true);
-        store2(dp_dst(DP_S1, 1), bZ + P, dp_dst(DP_M1, 1), bH1 + P, P);
+        store2(dp_dst(DP_S1, 0), bZ, dp_dst(DP_M1, 0), bH1, kFBuf);
         stores_read(FB_SR_P4);   // P6 may stage dz over dsp1
         // ---- G0 (dz += dm0 W0z, dm0 in H0) around F0 of the next tile (m0 -> S1, free since FB_TF_P4) ----
         wait_pd(FB_PD_P5 + 0, par);
         NVP_TL(it == 3, 71);
         gemm(bH0, S3, true);
-        store2(dp_dst(DP_M0, 0), bH0, nullptr, nullptr, P);
         if (has_next) {
           wait_pd(FB_ZFULL, par ^ 1);
           gemm(bA1, S1, false); gemm(bA1 + P, S1, true);
@@ -379,7 +376,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         NVP_TL(it == 3, 72);
         gemm(bH0 + P, S3, true);
         umma_commit(&bars[FB_AF_P6]);
-        store2(dp_dst(DP_M0, 1), bH0 + P, nullptr, nullptr, P);
+        store2(dp_dst(DP_M0, 0), bH0, nullptr, nullptr, kFBuf);
         stores_read(FB_SR_P5);   // the next tile's P0 may write h0 over dm0
         // dz, staged in Z by P6
         mbar_wait(&bars[FB_PD_P6], par);
@@ -520,12 +517,9 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       uint8_t* const bZ = buf_z(it);
       uint8_t* const bA1 = buf_a1(it);
       // ground truth of my row, fetched a few phases before it is needed
-      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (valid && a.dout == nullptr) {
-        g0 = (static_cast<float>(__ldg(a.gt + s * 3)) - 127.5f) / 127.5f;
-        g1 = (static_cast<float>(__ldg(a.gt + s * 3 + 1)) - 127.5f) / 127.5f;
-        g2 = (static_cast<float>(__ldg(a.gt + s * 3 + 2)) - 127.5f) / 127.5f;
-      }
+      // (raw bytes: nothing depends on them until P2, so the loads stay in flight behind the phases before it)
+      uint8_t g0 = 0, g1 = 0, g2 = 0;
+      if (valid && a.dout == nullptr) { g0 = __ldg(a.gt + s * 3); g1 = __ldg(a.gt + s * 3 + 1); g2 = __ldg(a.gt + s * 3 + 2); }
 
       // ---------------- P0: h0 = lrelu(m0 + b), a0 = sin(w0 (w tau + b)) h0 ----------------
       // writes H0 (dm0 of the previous tile: read by G0, done) and A0 (dsp0 of the previous tile: reducers)
@@ -628,7 +622,9 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         if (a.dout != nullptr) {
           d0 = __ldg(a.dout + s * 3) * gs; d1 = __ldg(a.dout + s * 3 + 1) * gs; d2 = __ldg(a.dout + s * 3 + 2) * gs;
         } else {
-          const float e0 = rgb0 - g0, e1 = rgb1 - g1, e2 = rgb2 - g2;
+          const float e0 = rgb0 - (static_cast<float>(g0) - 127.5f) / 127.5f;
+          const float e1 = rgb1 - (static_cast<float>(g1) - 127.5f) / 127.5f;
+          const float e2 = rgb2 - (static_cast<float>(g2) - 127.5f) / 127.5f;
           if (sub == 0) loss_acc += e0 * e0 + e1 * e1 + e2 * e2;
           d0 = e0 * loss_mult; d1 = e1 * loss_mult; d2 = e2 * loss_mult;
         }
