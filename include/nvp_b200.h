@@ -17,6 +17,8 @@
  *     library never allocates or frees device memory and keeps no global device state.
  *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; they never synchronise.
  *   - Gradients are ACCUMULATED into the caller's buffers (the caller zeroes them).
+ *   - Alignment: the keyframe and sparse-grid parameter and gradient buffers must be 16-byte aligned (the grid kernels
+ *     use 16-byte vector loads and reductions on them; checked, error code on violation).  torch allocations are.
  *   - Every function returns 0 on success, nonzero on error; nvp_last_error() returns a message
  *     (thread-local).  Nothing is thrown across the boundary.  There is no CPU path: host pointers
  *     are rejected where the driver can tell.

@@ -44,6 +44,11 @@ cudaEvent_t take_grid_event() {
   g_grid_event = nullptr;
   return e;
 }
+// Clears the registered event when a backward call leaves without having consumed it (early return, validation error):
+// a stale handle must never be recorded by a later call.
+struct GridEventGuard {
+  ~GridEventGuard() { g_grid_event = nullptr; }
+};
 
 int validate_desc(const nvp_desc* d) {
   NVP_CHECK(d != nullptr, "nvp_desc is NULL");
@@ -91,6 +96,21 @@ static int check_device_ptr(const void* p, const char* name) {
   return 0;
 }
 
+// The grid kernels read and reduce keyframe / sparse-grid entries with 16-byte vector accesses.
+static int check_align16(const void* p, const char* name) {
+  NVP_CHECK((reinterpret_cast<uintptr_t>(p) & 15u) == 0, std::string(name) + " must be 16-byte aligned");
+  return 0;
+}
+
+static int check_grid_grads(const nvp_grads* g) {
+  int rc;
+  if (g->kf_xy && (rc = check_align16(g->kf_xy, "grads.kf_xy"))) return rc;
+  if (g->kf_yt && (rc = check_align16(g->kf_yt, "grads.kf_yt"))) return rc;
+  if (g->kf_xt && (rc = check_align16(g->kf_xt, "grads.kf_xt"))) return rc;
+  if (g->sparse && (rc = check_align16(g->sparse, "grads.sparse"))) return rc;
+  return 0;
+}
+
 static int check_params(const nvp_params* p) {
   NVP_CHECK(p != nullptr, "nvp_params is NULL");
   int rc;
@@ -98,6 +118,10 @@ static int check_params(const nvp_params* p) {
   if ((rc = check_device_ptr(p->kf_yt, "params.kf_yt"))) return rc;
   if ((rc = check_device_ptr(p->kf_xt, "params.kf_xt"))) return rc;
   if ((rc = check_device_ptr(p->sparse, "params.sparse"))) return rc;
+  if ((rc = check_align16(p->kf_xy, "params.kf_xy"))) return rc;
+  if ((rc = check_align16(p->kf_yt, "params.kf_yt"))) return rc;
+  if ((rc = check_align16(p->kf_xt, "params.kf_xt"))) return rc;
+  if ((rc = check_align16(p->sparse, "params.sparse"))) return rc;
   for (int i = 0; i < 3; ++i) {
     if ((rc = check_device_ptr(p->siren_w[i], "params.siren_w"))) return rc;
     if ((rc = check_device_ptr(p->siren_b[i], "params.siren_b"))) return rc;
@@ -241,6 +265,7 @@ static int fwd_bwd_common(const nvp_desc* d, const nvp_params* p, const float* c
                           float* loss_sum, float* out_rgb, void* workspace, size_t workspace_bytes, int mode,
                           void* stream) {
   reset_launch_count();
+  GridEventGuard event_guard;   // whatever happens below, the event registered for this call does not outlive it
   LevelTab tab;
   if (int rc = build_level_table(d, &tab, nullptr)) return rc;
   NVP_CHECK(n >= 0 && n_global >= n, "need 0 <= n <= n_global");
@@ -248,6 +273,7 @@ static int fwd_bwd_common(const nvp_desc* d, const nvp_params* p, const float* c
   if (n == 0) return 0;
   int rc;
   if ((rc = check_params(p))) return rc;
+  if ((rc = check_grid_grads(g))) return rc;
   if ((rc = check_device_ptr(coords, "coords"))) return rc;
   if ((rc = check_device_ptr(tsteps, "tsteps"))) return rc;
   if (gt_u8 && (rc = check_device_ptr(gt_u8, "gt_u8"))) return rc;

@@ -486,7 +486,8 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
     const int r = quarter * 32 + lane;          // row inside the tile
     const int pc = sub * C;                     // first column inside the panel
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const bool elected = (tid == 128);
+    const bool elected = (tid == 128);   // stamps the timeline (NVP_TIMELINE builds)
+    (void)elected;
     const float gs = __ldg(a.gscale), inv_gs = __ldg(a.gscale + 1), loss_mult = __ldg(a.gscale + 2);
     float loss_acc = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f;
 

@@ -1142,13 +1142,19 @@ TcWorkspace carve_tc(const nvp_desc* d, int64_t n, int what, void* base) {
   return w;
 }
 
+// SM count of the current device (cached per device index: a process may drive several, possibly different, GPUs).
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cache[kMaxDev];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < kMaxDev) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
   }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < kMaxDev) cache[dev].store(sms, std::memory_order_relaxed);
   return sms;
 }
 

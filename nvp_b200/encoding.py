@@ -36,6 +36,37 @@ class Encoding(nn.Module):
         g = torch.Generator().manual_seed(seed)
         self.params = nn.Parameter((torch.rand(n_params, generator=g) * 2 - 1) * 1e-4)
 
+    # ------------------------------------------------------------------------------------------
+    def padded_level_offsets(self):
+        """Level offsets (in cells) of upstream tiny-cuda-nn's layout, which pads every level to a multiple of 8 entries.
+        The reference's fork does not pad (compression.py:72,77 would fail otherwise); checkpoints written with an upstream
+        build do."""
+        off, out = 0, [0]
+        for res in self.level_res:
+            off += (res * res + 7) // 8 * 8
+            out.append(off)
+        return out
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        """Accept a `params` tensor in upstream tcnn's padded layout: the per-level padding entries are dropped (they are
+        never addressed by this implementation, whose flat index wraps modulo res^2 - SURVEY A.2); any other size
+        mismatch gets a message that names both layouts.  PARITY UNPINNED for that remap: no tcnn build is available to
+        check an upstream checkpoint against."""
+        key = prefix + "params"
+        t = state_dict.get(key)
+        if t is not None and t.numel() != self.params.numel():
+            padded = self.padded_level_offsets()
+            if t.numel() == padded[-1] * self.n_features:
+                flat = t.reshape(-1, self.n_features)
+                state_dict[key] = torch.cat([flat[padded[l]: padded[l] + self.level_res[l] ** 2]
+                                             for l in range(self.n_levels)]).reshape(-1).to(t.dtype)
+            else:
+                raise RuntimeError(
+                    f"{key}: got {t.numel()} values; expected {self.params.numel()} (level-major res^2*F entries, no padding: "
+                    f"the reference fork's layout) or {padded[-1] * self.n_features} (upstream tiny-cuda-nn, levels padded "
+                    f"to multiples of 8 entries)")
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """[N,2] in [0,1] -> [N, n_levels*F] (level-major), differentiable w.r.t. `.params` — the standalone
         tcnn.Encoding.__call__ of modules.py:65-67.  Runs the same gather / scatter kernels as the fused model:

@@ -45,6 +45,25 @@ def _require_cuda(name: str, t: torch.Tensor, dtype) -> torch.Tensor:
     return t.contiguous()
 
 
+def _check_out(name: str, t: Optional[torch.Tensor], like: torch.Tensor, numel: int) -> None:
+    """Output / accumulation buffers are handed to the library as raw pointers: validate what it cannot."""
+    if t is None:
+        return
+    if not t.is_cuda or t.device != like.device:
+        raise RuntimeError(f"{name} must live on {like.device} (got {t.device}); nvp_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if t.numel() != numel:
+        raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
+
+
+def _check_grads(params: Sequence[torch.Tensor], grads: Sequence[Optional[torch.Tensor]]) -> None:
+    for i, (p, g) in enumerate(zip(params, grads)):
+        _check_out(f"gradient of {PARAM_ORDER[i]}", g, p, p.numel())
+
+
 class _Workspace:
     """Grow-only per-device scratch handed to the library (the library never allocates)."""
 
@@ -100,6 +119,7 @@ def backward(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequence
     tsteps = _require_cuda("temporal_steps", tsteps, torch.float32)
     dout = _require_cuda("grad_output", dout, torch.float32)
     params = [_require_cuda(f"parameter {PARAM_ORDER[i]}", p.detach(), torch.float32) for i, p in enumerate(params)]
+    _check_grads(params, grads)
     n = coords.shape[0]
     with torch.cuda.device(coords.device):
         ws = WORKSPACE.get(coords.device, _lib.workspace_bytes(desc, n, mode, 1))
@@ -123,6 +143,9 @@ def fwd_loss_bwd(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], grads: Sequ
     gt_u8 = _require_cuda("img", gt_u8, torch.uint8)
     params = [_require_cuda(f"parameter {PARAM_ORDER[i]}", p.detach(), torch.float32) for i, p in enumerate(params)]
     n = coords.shape[0]
+    _check_grads(params, grads)
+    _check_out("loss_sum", loss_sum, coords, 1)
+    _check_out("out_rgb", out_rgb, coords, 3 * n)
     with torch.cuda.device(coords.device):
         ws = WORKSPACE.get(coords.device, _lib.workspace_bytes(desc, n, mode, 1))
         pp, gg = pack_ptrs(params), pack_ptrs(grads)

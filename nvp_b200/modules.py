@@ -106,9 +106,14 @@ class NVP(nn.Module):
             if not p.requires_grad:
                 grads.append(None)
                 continue
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-            grads.append(p.grad)
+            g = p.grad
+            if g is None or g.dtype != p.dtype or g.device != p.device or not g.is_contiguous() or g.shape != p.shape:
+                # the library accumulates through raw pointers: an incompatible .grad is replaced (keeping its value)
+                new = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                if g is not None:
+                    new.copy_(g)
+                p.grad = g = new
+            grads.append(g)
         if loss_sum is None:
             loss_sum = torch.zeros(1, dtype=torch.float32, device=coords.device)
         functional.fwd_loss_bwd(self.desc, ps, grads, coords, tsteps, gt, n_global or n, loss_sum, self.mode, out_rgb,

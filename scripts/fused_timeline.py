@@ -22,6 +22,10 @@ names = {0: "P0 acc ready", 16: "P0 start", 1: "P0 end", 2: "P1 acc ready", 17: 
          64: "mma: F1 z-part issue", 65: "mma: PD_P0[1] seen", 66: "mma: PD_P1[1] seen", 67: "mma: PD_P3[0] seen", 68: "mma: PD_P3[1] seen",
          69: "mma: PD_P4[0]+TF seen", 70: "mma: PD_P4[1] seen", 71: "mma: PD_P5[0] seen", 72: "mma: PD_P5[1] seen",
          80: "mma: AF_P1 committed", 81: "mma: AF_P2 committed", 82: "mma: AF_P4 committed", 83: "mma: AF_P5 committed"}
+names[15] = "next tile loop top"
+for wp in range(4, 20):
+    names[96 + wp] = f"  P5 end of warp {wp}"
+    names[32 + wp - 4] = f"  P1 end of warp {wp}"
 print("ring wait cycles of the MMA thread in this tile:", v[90]); v[90] = 0
 for k, tt in sorted(((k, x) for k, x in enumerate(v) if x), key=lambda kv: kv[1]):
     print(f"{tt - t0:8d}  {names.get(k, 'slot %d' % k)}")

@@ -68,3 +68,26 @@ def test_cpu_tensors_fail_loudly():
         m(x, temporal_interp=True)
     with pytest.raises(ValueError):
         nvp_b200.NVP(out_features=3, encoding_config=small_json(), mode="triton")
+
+
+def test_padded_tcnn_layout_is_remapped_or_rejected():
+    """a checkpoint whose keyframe params use upstream tiny-cuda-nn's padded level layout (every level rounded
+    up to 8 entries) is remapped on load; any other size gets an error naming both layouts.  (The remap itself is
+    'parity unpinned': no tcnn build exists here to produce such a checkpoint.)"""
+    import pytest
+    from nvp_b200.encoding import Encoding
+    cfg = {"otype": "DenseGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 24, "base_resolution": 16,
+           "per_level_scale": 1.35}
+    enc = Encoding(2, cfg)
+    ref = enc.params.detach().clone()
+    padded = enc.padded_level_offsets()
+    assert padded[2] - padded[1] == 488 and enc.level_res[1] ** 2 == 484   # level 1: 22^2 = 484 -> 488
+    big = torch.full((padded[-1], 2), 7.0)
+    for l in range(16):
+        n = enc.level_res[l] ** 2
+        big[padded[l]: padded[l] + n] = ref.reshape(-1, 2)[enc.level_offsets[l]: enc.level_offsets[l] + n]
+    enc2 = Encoding(2, cfg, seed=1)
+    enc2.load_state_dict({"params": big.reshape(-1)})
+    assert torch.equal(enc2.params.detach(), ref)
+    with pytest.raises(RuntimeError, match="padded"):
+        enc2.load_state_dict({"params": torch.zeros(123)})
