@@ -370,6 +370,76 @@ def nvp_loss_and_grads(p: Dict[str, torch.Tensor], coords: torch.Tensor, tsteps:
     return rgb.detach(), float(loss.detach()), grads
 
 
+def leaky_relu_margin(p: Dict[str, torch.Tensor], coords: torch.Tensor, cfg: NVPConfig, dtype=torch.float64, mma_dtype=None) -> torch.Tensor:
+    """min over the modulator's 3x128 units of |pre-activation|, per sample [N].  LeakyReLU's derivative jumps from 0.01
+    to 1 at zero (modulation.py:109-117), so a sample with a unit within round-off of zero has no well-defined gradient
+    for a comparison across arithmetics; tests use this to keep such samples out of max-norm gradient checks."""
+    with torch.no_grad():
+        z = latent_forward(p, coords.reshape(-1, 3), cfg).to(dtype)
+        q = {k: v.to(dtype) for k, v in p.items() if k not in PARAM_KEYS_GRID}
+        hs = modulator_forward(z, q, cfg.n_hidden_layers, mma_dtype)
+        margin = None
+        for h in hs:
+            m = torch.where(h >= 0, h, -h / 0.01).min(dim=1).values     # |m| recovered from h = lrelu(m)
+            margin = m if margin is None else torch.minimum(margin, m)
+    return margin
+
+
+def nvp_loss_and_grads_touched(p: Dict[str, torch.Tensor], coords: torch.Tensor, tsteps: torch.Tensor, gt_u8: torch.Tensor,
+                              cfg: NVPConfig, n_global: Optional[int] = None, dtype=torch.float64, mma_dtype=None):
+    """The same forward + MSE + backward as nvp_loss_and_grads for FULL-SIZE grids (600x300x300xF): the dense layers go
+    through autograd, the grid gradients are returned on the touched cells only (autograd of the gathers would build nine
+    dense 0.9-1.7 GB tensors: sparsegrid.py:61-69 backward = index_put(accumulate) per neighbour).
+
+    Returns (rgb, loss, mlp_grads, grid_grads, dz) with grid_grads[key] = (flat cell indices int64 [K] sorted unique,
+    values [K, F] in `dtype`): values[k] = sum over samples / corners of weight * dz, i.e. tcnn's kernel_grid_backward
+    (dparams[index] += w * dout) and the transpose of the 3x3 neighbourhood gather (sparsegrid.py:61-69).
+    dz [N, Z] is dL/dz (for size-independent checks: bilinear weights sum to one)."""
+    c = coords.reshape(-1, 3)
+    with torch.no_grad():
+        z0 = latent_forward(p, c, cfg)                  # gather + interpolation in the parameters' own precision
+    z = z0.to(dtype).requires_grad_(True)
+    q = {k: v.detach().to(dtype).requires_grad_(True) for k, v in p.items() if k not in PARAM_KEYS_GRID}
+    mods = modulator_forward(z, q, cfg.n_hidden_layers, mma_dtype)
+    rgb = siren_forward(tsteps.reshape(-1, 1).to(dtype), mods, q, cfg.n_hidden_layers, mma_dtype=mma_dtype)
+    gt = normalise_gt(gt_u8.reshape(-1, 3), dtype)
+    n = rgb.shape[0] if n_global is None else n_global
+    loss = ((rgb - gt) ** 2).sum() / (3.0 * n)
+    loss.backward()
+    dz = z.grad.detach()
+    mlp_grads = {k: v.grad for k, v in q.items()}
+    cn = c.detach().cpu().numpy()
+    tab, F2, F3, L = cfg.table, cfg.n_features, cfg.sparse_features, cfg.n_levels
+    pw = L * F2
+    grid_grads = {}
+
+    def accumulate(flat_idx: np.ndarray, contrib: np.ndarray):
+        uniq, inv = np.unique(flat_idx, return_inverse=True)
+        acc = np.zeros((uniq.shape[0], contrib.shape[1]), np.float64)
+        np.add.at(acc, inv, contrib)
+        return torch.from_numpy(uniq), torch.from_numpy(acc).to(dtype)
+
+    dzn = dz.double().numpy()
+    # concat order xy, yt, xt (modules.py:69); plane inputs xy=(x,y), yt=(t,y), xt=(t,x) (modules.py:61-63)
+    for k, (key, cols) in enumerate((("keyframes_xy.params", [1, 2]), ("keyframes_yt.params", [0, 2]), ("keyframes_xt.params", [0, 1]))):
+        idx, w = dense_grid_indices(cn[:, cols], tab)                         # [N, L, 4]
+        d = dzn[:, k * pw:(k + 1) * pw].reshape(-1, L, 1, F2)                  # [N, L, 1, F]
+        contrib = (w.astype(np.float64)[..., None] * d).reshape(-1, F2)        # [N*L*4, F]
+        grid_grads[key] = accumulate(idx.reshape(-1), contrib)
+    ti, xi, yi = sparse_grid_indices(cn, cfg.t_resolution, cfg.x_resolution, cfg.y_resolution)
+    X, Y = cfg.x_resolution, cfg.y_resolution
+    flat, contrib = [], []
+    v = 0
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            vx, vy = np.clip(xi + i, 0, X - 1), np.clip(yi + j, 0, Y - 1)
+            flat.append((ti * X + vx) * Y + vy)
+            contrib.append(dzn[:, 3 * pw + v * F3: 3 * pw + (v + 1) * F3])
+            v += 1
+    grid_grads["sparse_grid.embeddings"] = accumulate(np.concatenate(flat), np.concatenate(contrib))
+    return rgb.detach(), float(loss.detach()), mlp_grads, grid_grads, dz
+
+
 # --------------------------------------------------------------------------------------------
 # Sampler (dataio.py:85-120) and synthetic video (SURVEY 8(d))
 # --------------------------------------------------------------------------------------------

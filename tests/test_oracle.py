@@ -100,3 +100,30 @@ def test_forward_is_linear_in_last_layer_and_loss_scales_with_n_global():
     _, l2, g2 = O.nvp_loss_and_grads(p, coords, tau, gt, cfg, n_global=128)
     assert abs(l1 - 2 * l2) < 1e-7
     assert torch.allclose(g1["net.last_layer.weight"], 2 * g2["net.last_layer.weight"], atol=1e-9)
+
+
+def test_touched_cells_gradients_equal_dense_autograd():
+    """nvp_loss_and_grads_touched (used by the full-size GPU parity tests) == nvp_loss_and_grads on a grid small enough for
+    dense autograd: same loss, same 14 dense-layer gradients, same grid gradients on the touched cells, zero elsewhere."""
+    from tests.helpers import sampler_like_inputs
+    cfg = O.NVPConfig(t_resolution=7, x_resolution=33, y_resolution=29)
+    p = {k: v.double() for k, v in O.init_params(cfg, seed=3, grid_std=0.3).items()}
+    coords, tsteps, gt = sampler_like_inputs(cfg, 2000, seed=1)
+    rgb, loss, grads = O.nvp_loss_and_grads(p, coords, tsteps, gt, cfg, dtype=torch.float64)
+    rgb2, loss2, mg, gg, dz = O.nvp_loss_and_grads_touched(p, coords, tsteps, gt, cfg)
+    assert abs(loss - loss2) < 1e-15 and float((rgb - rgb2).abs().max()) < 1e-14
+    for k, v in mg.items():
+        assert float((v - grads[k]).abs().max()) <= 1e-14 * float(grads[k].abs().max()), k
+    for k, (idx, val) in gg.items():
+        F = cfg.n_features if "keyframes" in k else cfg.sparse_features
+        dense = grads[k].reshape(-1, F)
+        assert float((dense[idx] - val).abs().max()) <= 1e-13 * float(dense.abs().max()), k
+        rest = torch.ones(dense.shape[0], dtype=torch.bool)
+        rest[idx] = False
+        assert float(dense[rest].abs().sum()) == 0.0, k
+    # bilinear weights sum to one: a plane's gradient mass per feature equals the sum of its dz columns
+    pw = cfg.n_levels * cfg.n_features
+    for k, key in enumerate(("keyframes_xy.params", "keyframes_yt.params", "keyframes_xt.params")):
+        mass = gg[key][1].sum(dim=0)
+        want = dz[:, k * pw:(k + 1) * pw].reshape(-1, cfg.n_levels, cfg.n_features).sum(dim=(0, 1))
+        assert float((mass - want).abs().max()) <= 1e-8 * float(dz.abs().sum())   # the fp32 weights sum to one to 1e-7
