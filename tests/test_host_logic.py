@@ -144,3 +144,62 @@ def test_two_rank_gloo_grid_first_all_reduce_equals_one_all_reduce():
         out = mgr.dict()
         mp.spawn(_grid_first_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_slab_routing_partitions_the_reference_batch():
+    """trainer.route_to_slab: every sample goes to exactly one rank, the one owning the frame SparseGrid.forward reads
+    (sparsegrid.py:43-46, restated by the oracle), for video lengths equal to and different from the grid's t_resolution."""
+    from nvp_b200 import trainer
+    from nvp_b200.dist import t_slab
+    for T_video, t_res, world in ((600, 600, 8), (8, 600, 4), (300, 300, 3), (17, 5, 2)):
+        g = torch.Generator().manual_seed(T_video)
+        n = 20000
+        t_idx = torch.randint(0, T_video, (n,), generator=g)
+        coords = torch.stack((torch.linspace(0, 1, T_video)[t_idx], torch.rand(n, generator=g), torch.rand(n, generator=g)), dim=1)
+        coords[:3, 0] = torch.tensor([0.0, 1.0, 0.5])
+        x = {"all_coords": coords[None], "temporal_steps": torch.rand(1, n, generator=g)}
+        gt = torch.randint(0, 256, (1, n, 3), generator=g, dtype=torch.uint8)
+        frames = torch.from_numpy(O.sparse_grid_indices(coords.numpy(), t_res, 4, 4)[0])
+        assert torch.equal(trainer.nearest_frame(coords[:, 0], t_res), frames)
+        total, seen = 0, torch.zeros(n, dtype=torch.int32)
+        for r in range(world):
+            xi, gi = trainer.route_to_slab(x, gt, t_res, r, world)
+            lo, hi = t_slab(t_res, r, world)
+            fr = trainer.nearest_frame(xi["all_coords"][0, :, 0], t_res)
+            assert bool(((fr >= lo) & (fr < hi)).all())
+            keep = (frames >= lo) & (frames < hi)
+            assert torch.equal(xi["all_coords"][0], coords[keep]) and torch.equal(gi[0], gt[0][keep])
+            assert torch.equal(xi["temporal_steps"][0], x["temporal_steps"][0][keep])
+            seen += keep.int()
+            total += int(keep.sum())
+        assert total == n and bool((seen == 1).all())
+
+
+def _slab_sync_worker(rank, world, port, out):
+    import types
+    import torch.distributed as dist
+    from nvp_b200 import trainer
+    from nvp_b200.dist import t_slab
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T = 7
+    truth = torch.arange(T * 3 * 2 * 2, dtype=torch.float32).reshape(T, 3, 2, 2)
+    emb = torch.full_like(truth, -1.0)                    # stale copy everywhere ...
+    lo, hi = t_slab(T, rank, world)
+    emb[lo:hi] = truth[lo:hi]                             # ... except the frames this rank owns and keeps up to date
+    tr = object.__new__(trainer.FusedTrainer)
+    tr.distributed, tr._synced, tr.world, tr.group, tr.t_resolution = True, False, world, None, T
+    tr.model = types.SimpleNamespace(sparse_grid=types.SimpleNamespace(embeddings=torch.nn.Parameter(emb)))
+    tr.sync_slabs()
+    out[rank] = bool(torch.equal(tr.model.sparse_grid.embeddings.data, truth))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_slab_gather_completes_the_grid():
+    """Checkpoints of a slab-trained model (training.py:36,66,90): after sync_slabs every rank holds every owner's frames."""
+    import torch.multiprocessing as mp
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_slab_sync_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))
