@@ -36,7 +36,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_SAMPLES = 1245184            # dataio.py:91
-VIDEO = (600, 1080, 1920)      # T, H, W
+VIDEOS = {"1080p": (600, 1080, 1920), "4k": (600, 2160, 3840)}   # T, H, W (BASELINE.json configs[2..4])
+VIDEO = VIDEOS["1080p"]
 METRIC = "Mpixels/sec fwd+bwd @1920x1080x600"
 UNIT = "Mpixels/s"
 
@@ -47,11 +48,11 @@ def load_config(name: str) -> dict:
         return json.load(f)["nvp"]
 
 
-def synth_batch(n: int, seed: int, t_range=None):
+def synth_batch(n: int, seed: int, t_range=None, video=None):
     """One sampler batch (dataio.py:104-120) over a virtual synthetic video: the pixel value is a smooth
     pattern plus hash noise evaluated at the sampled (t,row,col) — the 3.7 GB video is never materialised.
     t_range=(lo,hi) restricts the frame index to a rank's t-slab (stratified version of the uniform sampler)."""
-    T, Hh, Ww = VIDEO
+    T, Hh, Ww = video or VIDEO
     g = torch.Generator().manual_seed(seed)
     lo, hi = t_range if t_range is not None else (0, T)
     t_idx = torch.randint(lo, hi, (n,), generator=g)
@@ -151,6 +152,7 @@ def algorithmic_work(F: int):
         "mlp_forward": ("tensor", 2 * fwd_mac),
         "mlp_backward": ("tensor", 2 * (fwd_mac - 128)),   # dgrad (none to the scalar SIREN input)
         "mlp_wgrad": ("tensor", 2 * fwd_mac),
+        "mlp_fused": ("tensor", 2 * fwd_mac + 2 * (fwd_mac - 128)),   # forward + dgrad in one kernel
         "total_bytes": 2 * G + 31, "total_flop": 3 * 2 * fwd_mac - 2 * 128,
     }
 
@@ -180,15 +182,17 @@ def run_reference(args):
         return
     cfg_json = load_config(args.config)
     n_sample = N_SAMPLES // 4
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    # --steps / --warmup are honoured up to a cap that keeps the run within a few minutes (a step is ~5-15 s of CPU work)
+    steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 3))
     t = cpu_port_step_time(cfg_json, n_sample, steps, warmup)
     v = n_sample / t / 1e6
     cores = os.cpu_count() or 1
-    sample = f"{n_sample} of {N_SAMPLES} coordinates per step (1/4 batch), {steps} timed steps after {warmup} warm-up"
+    sample = (f"{n_sample} of {N_SAMPLES} coordinates per step (1/4 batch), {steps} timed steps after {warmup} warm-up"
+              + (f" (asked: --steps {args.steps} --warmup {args.warmup}; capped at 12 / 3)" if (steps, warmup) != (args.steps, args.warmup) else ""))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": bench_config(args, "cpu oracle port"),
+        "data": "synthetic", "config": dict(bench_config(args, "cpu oracle port"), reference_sample=sample),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = pure-PyTorch CPU path restated by oracle/ (tiny-cuda-nn DenseGrid restated; see DESIGN.md)",
@@ -196,9 +200,14 @@ def run_reference(args):
 
 
 def bench_config(args, mode):
-    return {"workload": f"synthetic 1920x1080x600 (UVG Jockey stand-in), config_nvp_{args.config}, "
-                        f"{N_SAMPLES} sampled coordinates per step per GPU",
-            "nvp_config": f"config_nvp_{args.config}", "samples_per_step_per_gpu": N_SAMPLES, "mode": mode,
+    T, Hh, Ww = VIDEOS[args.video]
+    strong = args.gpus > 1 and args.scaling == "strong"
+    per = (f"{N_SAMPLES} sampled coordinates per step GLOBALLY (the reference's batch, dataio.py:91), split over the GPUs by "
+           "ownership of the 3-D grid's frames" if strong else f"{N_SAMPLES} sampled coordinates per step per GPU")
+    return {"workload": f"synthetic {Ww}x{Hh}x{T} ({'UVG Jockey stand-in' if args.video == '1080p' else 'synthetic 4K'}), "
+                        f"config_nvp_{args.config}, {per}",
+            "nvp_config": f"config_nvp_{args.config}", "video": args.video, "scaling": args.scaling if args.gpus > 1 else "n/a (1 GPU)",
+            "samples_per_step_per_gpu": N_SAMPLES // args.gpus if strong else N_SAMPLES, "mode": mode,
             "step": "grad-buffer zero + sample bucketing + grid gather + fused MLP fwd + L2 loss + fused bwd + grid scatter-add + wgrad"
                     + ((" + NCCL all-reduce of the whole flat gradient buffer" if args.full_allreduce else
                         " + NCCL all-reduce of keyframe+MLP gradients (sparse 3-D grid owned per rank by t-slab, samples "
@@ -213,7 +222,7 @@ def run_ours(args):
     import torch.distributed as dist
     import nvp_b200
     from nvp_b200 import _lib, functional
-    from nvp_b200.optim import FusedAdamW, flatten_parameters
+    from nvp_b200.trainer import FusedTrainer, route_to_slab
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,30 +238,44 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
     cfg_json = load_config(args.config)
+    video = VIDEOS[args.video]
     torch.manual_seed(0)
     model = nvp_b200.NVP(type="nvp", out_features=3, encoding_config=cfg_json, mode=args.mode).to(dev)
-    if world > 1:
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-    # t-slab ownership of the sparse grid: its gradient sits at the end of the flat buffer and is
-    # excluded from the all-reduce; every rank samples frames of its own slab only.
+    # The product's training step (nvp_b200.trainer): flat parameter / gradient buffers, and with several GPUs t-slab
+    # ownership of the sparse grid: its gradient sits at the end of the flat buffer, outside the
+    # all-reduce, and each rank takes the samples of its own frames.  --full-allreduce: replicated everything instead.
     slab = world > 1 and not args.full_allreduce
-    flat_params, flat = flatten_parameters(model, last=[model.sparse_grid.embeddings] if slab else ())
-    reduce_view = flat[:flat.replicated_numel] if slab else flat
-    t_range = None
-    if slab:
-        from nvp_b200.dist import t_slab
-        t_range = t_slab(cfg_json["3d_encoding"]["t_resolution"], rank, world)
-        assert cfg_json["3d_encoding"]["t_resolution"] == VIDEO[0]
-    n, n_global = N_SAMPLES, N_SAMPLES * world
+    trainer = FusedTrainer(model, lr=1e-2, total_steps=100000, distributed=slab)
+    if world > 1 and not slab:
+        from nvp_b200.dist import broadcast_parameters
+        broadcast_parameters(model, 0)
+    flat_params, flat = trainer.flat_params, trainer.flat_grads
+    reduce_view = trainer.reduce_view if slab else flat
+    t_res = cfg_json["3d_encoding"]["t_resolution"]
+    strong = world > 1 and args.scaling == "strong"
+    n_global = N_SAMPLES if strong else N_SAMPLES * world
     F = cfg_json["2d_encoding_xy"]["n_features_per_level"]
 
     n_pool = 8
     host = []
     for i in range(n_pool):
-        c, t, g = synth_batch(n, 1000 * rank + i, t_range)
+        if strong:
+            # the SAME global batch on every rank (the reference's sampler stream), each rank keeps the samples whose
+            # nearest grid frame it owns: the union over ranks is the one-GPU batch
+            c, t, g = synth_batch(N_SAMPLES, i, None, video)
+            if slab:
+                x, gg = route_to_slab({"all_coords": c[None], "temporal_steps": t[None]}, g[None], t_res, rank, world)
+                c, t, g = x["all_coords"][0].contiguous(), x["temporal_steps"][0].contiguous(), gg[0].contiguous()
+            else:
+                from nvp_b200.dist import shard_range
+                lo, hi = shard_range(N_SAMPLES, rank, world)
+                c, t, g = c[lo:hi].contiguous(), t[lo:hi].contiguous(), g[lo:hi].contiguous()
+        else:
+            assert not slab or t_res == video[0]
+            c, t, g = synth_batch(N_SAMPLES, 1000 * rank + i, trainer.slab if slab else None, video)
         host.append((c.pin_memory(), t.pin_memory(), g.pin_memory()))
     resident = [(c.to(dev), t.to(dev), g.to(dev)) for c, t, g in host]
+    n_local = sum(c.shape[0] for c, _, _ in host) / n_pool
     loss_sum = torch.zeros(1, device=dev)
     launches = [0]
 
@@ -302,12 +325,12 @@ def run_ours(args):
     kern = _lib.profile_read()
     _lib.profile_enable(False)
     gpu_launches = launches[0]
-    loss_last = float(loss_sum) / (3.0 * n)
+    loss_last = float(loss_sum) / (3.0 * n_local)
 
     # ---- end-to-end through the public API with host buffers
-    # every step's inputs start in pinned HOST memory; nvp_b200.dataio.DevicePrefetcher (the loop a user of
-    # training.train gets) copies batch i+1 on a side stream while step i computes.  All K copies, K steps and K
-    # loss read-backs happen inside the timed region; the first copy is not overlapped with anything.
+    # every step's inputs start in pinned HOST memory; nvp_b200.dataio.DevicePrefetcher -- the host->device stage of
+    # nvp_b200.training.train's loop -- copies batch i+1 on a side stream while step i computes.  All K copies, K steps
+    # and K loss read-backs happen inside the timed region; the first copy is not overlapped with anything.
     from nvp_b200.dataio import DevicePrefetcher
 
     def host_batches():
@@ -341,21 +364,25 @@ def run_ours(args):
     torch.cuda.synchronize()
     clocks = sampler.stop()
 
-    # ---- second line: the same step followed by the fused AdamW update (which also clears the gradients)
-    fopt = FusedAdamW(flat_params, flat, lr=1e-2, weight_decay=1e-3, t_max=100000, eta_min=1e-5)
-
-    def step_opt(i):
-        c, t, g = resident[i % n_pool]
-        loss_sum.zero_()
-        model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum,
-                           grid_event=overlap.event if overlap else None)
-        if overlap:
-            overlap.run()
-        elif world > 1:
-            dist.all_reduce(reduce_view)
-        fopt.step(zero_grad=True)
-
+    # ---- second line: the whole training step of nvp_b200.training.train -- FusedTrainer.step: the same
+    # fwd + loss + bwd (+ all-reduce) followed by the fused AdamW update, which also clears the gradients.  With t-slabs
+    # each rank updates the replicated parameters and the frames it owns only.
     flat.zero_()
+    if slab or world == 1:
+        def step_opt(i):
+            c, t, g = resident[i % n_pool]
+            trainer.step({"all_coords": c[None], "temporal_steps": t[None]}, g[None], n_global=n_global, routed=True)
+    else:
+        from nvp_b200.optim import FusedAdamW
+        fopt = FusedAdamW(flat_params, flat, lr=1e-2, weight_decay=1e-3, t_max=100000, eta_min=1e-5)
+
+        def step_opt(i):
+            c, t, g = resident[i % n_pool]
+            loss_sum.zero_()
+            model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum)
+            dist.all_reduce(flat)
+            fopt.step(zero_grad=True)
+
     for i in range(3):
         step_opt(i)
     ms_opt = timed(step_opt, args.steps)
@@ -375,7 +402,7 @@ def run_ours(args):
             ent = {"launches_per_step": cnt / args.steps, "ms_per_step": per_step, "share_of_step": ms / ms_total}
             if name in work:
                 bound, per_px = work[name]
-                per_step_work = per_px * n
+                per_step_work = per_px * n_local
                 if bound == "hbm":
                     ent.update(bound="hbm", achieved=per_step_work / (per_step * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
                 else:
@@ -388,20 +415,23 @@ def run_ours(args):
         d = kernels[dom]
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
                     "frac": d["frac"], "traffic": d["traffic"], "peak_source": peaks["source"],
-                    "note": "achieved = algorithmic bytes (SURVEY 8(d): every gathered/scattered element once) / CUDA-event time of the "
-                            "kind per step; traffic = ncu dram bytes per step from profiles/ (null if no capture for this config)",
-                    "whole_step": {"hbm_frac": work["total_bytes"] * n / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                   "tensor_frac": work["total_flop"] * n / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]}}
+                    "note": "achieved = algorithmic bytes / flops (SURVEY 8(d): every gathered/scattered element once; dense layers 2 "
+                            "FLOP per MAC) / CUDA-event time of the kind per step; traffic = ncu dram bytes per step from profiles/ "
+                            "(null if no capture for this config)",
+                    "whole_step": {"hbm_frac": work["total_bytes"] * n_local / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "tensor_frac": work["total_flop"] * n_local / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"]}}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.mode == "tc" else "f32",
             "data": "synthetic", "config": bench_config(args, "tc_f16" if args.mode == "tc" else "fp32_simt"),
-            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": 19 * n, "d2h_bytes_per_step": 4,
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(19 * n_local), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "with_optimizer": {"value": n_global / (ms_opt / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_opt / args.steps,
-                               "what": "same step + fused AdamW (exact torch.optim.AdamW semantics, gradient clear folded in) over all "
-                                       f"{flat_params.numel()} parameters"},
+                               "what": "nvp_b200.trainer.FusedTrainer.step: the same step + fused AdamW (exact torch.optim.AdamW "
+                                       "semantics, gradient clear folded in)" + (f"; each rank updates the {reduce_view.numel()} replicated "
+                                       f"parameters and its own 1/{world} of the sparse grid" if slab else
+                                       f" over all {flat_params.numel()} parameters")},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "loss_last_step": loss_last,
         }
@@ -424,6 +454,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="s", choices=["s", "l"])
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"])
+    ap.add_argument("--video", default="1080p", choices=sorted(VIDEOS), help="coordinate grid of the synthetic video (configs[4]: 4k)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = 1,245,184 samples per GPU; strong = the reference's 1,245,184 samples per step split over "
+                         "the GPUs (same sample set as one GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-allreduce", action="store_true", help="N>1: all-reduce the whole gradient (no t-slab ownership)")
     ap.add_argument("--overlap", action="store_true",

@@ -187,8 +187,9 @@ int nvp_sample_batch(const uint8_t* video, int T, int H, int W, const float* tem
  * After nvp_profile_enable(1) every kernel the library enqueues on this thread is bracketed by an
  * event pair; nvp_profile_read synchronises those events, returns per-kind totals and resets.
  * Kinds: 0 weight pack, 1 grid gather, 2 MLP forward, 3 MLP backward (dgrad), 4 MLP wgrad,
- *        5 grid scatter, 6 fp32-mode kernels, 7 misc.  No reference counterpart. */
-#define NVP_PROFILE_KINDS 8
+ *        5 grid scatter, 6 fp32-mode kernels, 7 misc, 8 sample bucketing, 9 fused MLP forward+loss+backward.
+ * No reference counterpart. */
+#define NVP_PROFILE_KINDS 10
 int nvp_profile_enable(int on);
 int nvp_profile_read(int max_kinds, float* total_ms, int* counts);
 

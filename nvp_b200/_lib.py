@@ -138,7 +138,8 @@ def grid_bin_plan(desc: NvpDesc, n: int) -> dict:
             "workspace": int(ws.value)}
 
 
-PROFILE_KINDS = ("pack", "grid_gather", "mlp_forward", "mlp_backward", "mlp_wgrad", "grid_scatter", "fp32_mode", "misc", "grid_bin")
+PROFILE_KINDS = ("pack", "grid_gather", "mlp_forward", "mlp_backward", "mlp_wgrad", "grid_scatter", "fp32_mode", "misc", "grid_bin",
+                 "mlp_fused")
 
 
 def profile_enable(on: bool) -> None:

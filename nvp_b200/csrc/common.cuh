@@ -47,7 +47,7 @@ cudaEvent_t take_grid_event();
   } while (0)
 
 // Optional per-kernel CUDA-event timing (nvp_profile_enable / nvp_profile_read in the C ABI).
-enum KernelId { K_PACK = 0, K_GATHER, K_MLP_FWD, K_MLP_BWD, K_MLP_WGRAD, K_SCATTER, K_SIMT, K_MISC, K_BIN, K_COUNT };
+enum KernelId { K_PACK = 0, K_GATHER, K_MLP_FWD, K_MLP_BWD, K_MLP_WGRAD, K_SCATTER, K_SIMT, K_MISC, K_BIN, K_MLP_FUSED, K_COUNT };
 void prof_start(int id, cudaStream_t st);
 void prof_stop(cudaStream_t st);
 struct ScopedKernelTimer {

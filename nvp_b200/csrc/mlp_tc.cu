@@ -1305,7 +1305,7 @@ int tc_fwd_bwd(const nvp_desc* d, const LevelTab& tab, const nvp_params* p, cons
     const size_t smem = fused_smem_layout().total + 1024;
     static_assert(fused_smem_layout().total + 1024 <= 227 * 1024, "fused kernel: shared-memory plan exceeds 227 KiB");
     NVP_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    ScopedKernelTimer timer(K_MLP_BWD, st);
+    ScopedKernelTimer timer(K_MLP_FUSED, st);
     mlp_fused_kernel<<<std::min(n_tiles, num_sms()), kFThreads, smem, st>>>(f);
     NVP_LAUNCH_CHECK();
   } else {
