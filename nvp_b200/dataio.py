@@ -170,7 +170,8 @@ class DevicePrefetcher:
         with torch.cuda.stream(self.copy_stream):
             if self.done[k] is not None:
                 self.copy_stream.wait_event(self.done[k])      # the step that read this slot has finished
-            if self.slots[k] is None:
+            if self.slots[k] is None or any(d.shape != t.shape or d.dtype != t.dtype for d, t in zip(self.slots[k], host)):
+                # (batch sizes vary when a global batch is routed to t-slab owners: trainer.route_to_slab)
                 self.slots[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
             for dst, src in zip(self.slots[k], host):
                 dst.copy_(src if src.is_pinned() else src.pin_memory(), non_blocking=True)
