@@ -29,7 +29,7 @@ shutil.copyfile(launches, os.path.join(root, f"{tag}_launches.csv"))
 
 kind_of = {"grid_binned_kernel<2, 0": "grid_gather", "grid_binned_kernel<4, 0": "grid_gather", "grid_binned_kernel<2, 1": "grid_scatter",
            "grid_binned_kernel<4, 1": "grid_scatter", "gather_": "grid_gather", "grid_gather": "grid_gather", "scatter": "grid_scatter",
-           "mlp_forward": "mlp_forward", "mlp_backward": "mlp_backward", "mlp_wgrad": "mlp_wgrad", "grid_bin_": "grid_bin",
+           "mlp_fused": "mlp_fused", "mlp_forward": "mlp_forward", "mlp_backward": "mlp_backward", "mlp_wgrad": "mlp_wgrad", "grid_bin_": "grid_bin",
            "pack_weights": "pack"}
 ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}

@@ -2,7 +2,7 @@
 import sys, torch
 sys.path.insert(0, '.')
 import bench, nvp_b200
-cfg = bench.load_config("s")
+cfg = bench.load_config(sys.argv[2] if len(sys.argv) > 2 else "s")
 torch.manual_seed(0)
 m = nvp_b200.NVP(out_features=3, encoding_config=cfg, mode="tc").cuda()
 from nvp_b200.optim import flatten_parameters
