@@ -224,6 +224,7 @@ def run_ours(args):
     from nvp_b200 import _lib, functional
     from nvp_b200.trainer import FusedTrainer, route_to_slab
 
+    t_start = time.time()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -276,6 +277,11 @@ def run_ours(args):
         host.append((c.pin_memory(), t.pin_memory(), g.pin_memory()))
     resident = [(c.to(dev), t.to(dev), g.to(dev)) for c, t, g in host]
     n_local = sum(c.shape[0] for c, _, _ in host) / n_pool
+
+    def trace(msg):
+        if os.environ.get("NVP_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg} ({time.time() - t_start:.1f} s)", file=sys.stderr, flush=True)
+    trace(f"pool ready, {n_local:.0f} samples per step on this rank")
     loss_sum = torch.zeros(1, device=dev)
     launches = [0]
 
@@ -317,6 +323,7 @@ def run_ours(args):
     # ---- device-resident measurement (value) with live per-kernel timing
     for i in range(args.warmup):
         step(*resident[i % n_pool])
+    trace("warm-up done")
     sampler = ClockSampler(local)
     launches[0] = 0
     _lib.profile_enable(True)
@@ -326,6 +333,7 @@ def run_ours(args):
     _lib.profile_enable(False)
     gpu_launches = launches[0]
     loss_last = float(loss_sum) / (3.0 * n_local)
+    trace("timed region done")
 
     # ---- end-to-end through the public API with host buffers
     # every step's inputs start in pinned HOST memory; nvp_b200.dataio.DevicePrefetcher -- the host->device stage of
@@ -363,6 +371,7 @@ def run_ours(args):
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    trace("end-to-end leg done")
 
     # ---- second line: the whole training step of nvp_b200.training.train -- FusedTrainer.step: the same
     # fwd + loss + bwd (+ all-reduce) followed by the fused AdamW update, which also clears the gradients.  With t-slabs
@@ -386,6 +395,7 @@ def run_ours(args):
     for i in range(3):
         step_opt(i)
     ms_opt = timed(step_opt, args.steps)
+    trace("optimiser leg done")
 
     if rank == 0:
         ms_step = ms_total / args.steps
