@@ -397,6 +397,26 @@ def run_ours(args):
     ms_opt = timed(step_opt, args.steps)
     trace("optimiser leg done")
 
+    # ---- third line: the reference's own call sequence (training.py:47-52,74), unfused: model(x) -> image_mse in torch ->
+    # loss.backward().  The forward runs the inference kernels, the backward recomputes it inside the fused kernel; gradients
+    # are accumulated straight into .grad (functional.NvpFunction).
+    ms_api = None
+    if world == 1:
+        from nvp_b200.loss_functions import image_mse
+
+        def step_api(i):
+            c, t, g = resident[i % n_pool]
+            flat.zero_()
+            out = model({"all_coords": c[None], "temporal_steps": t[None]})
+            gt = {"img": ((g.float() - 127.5) / 127.5)[None]}
+            image_mse(None, out, gt)["img_loss"].mean().backward()
+
+        for i in range(3):
+            step_api(i)
+        ms_api = timed(step_api, args.steps)
+        flat.zero_()
+        trace("unfused API leg done")
+
     if rank == 0:
         ms_step = ms_total / args.steps
         value = n_global / (ms_step * 1e-3) / 1e6
@@ -442,6 +462,10 @@ def run_ours(args):
                                        "semantics, gradient clear folded in)" + (f"; each rank updates the {reduce_view.numel()} replicated "
                                        f"parameters and its own 1/{world} of the sparse grid" if slab else
                                        f" over all {flat_params.numel()} parameters")},
+            "unfused_api": None if ms_api is None else {
+                "value": n_global / (ms_api / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_api / args.steps,
+                "what": "model(x) -> loss_functions.image_mse (torch) -> loss.backward(): the reference's own sequence through the "
+                        "drop-in nn.Module and autograd (forward kernels + recomputing fused backward + torch's loss kernels)"},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "loss_last_step": loss_last,
         }

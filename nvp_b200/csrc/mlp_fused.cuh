@@ -106,6 +106,7 @@ __global__ void fused_consts_kernel(FusedConsts* out, const float* b0, const flo
 #ifndef NVP_ABL
 #define NVP_ABL 0
 #endif
+
 #if NVP_ABL & 4
 #define F_STORE(...) do {} while (0)
 #else
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
       uint8_t* const bA1 = buf_a1(it);
       // ground truth of my row, fetched a few phases before it is needed
       // (raw bytes: nothing depends on them until P2, so the loads stay in flight behind the phases before it)
-      uint8_t g0 = 0, g1 = 0, g2 = 0;
+      uint32_t g0 = 0, g1 = 0, g2 = 0;
       if (valid && a.dout == nullptr) { g0 = __ldg(a.gt + s * 3); g1 = __ldg(a.gt + s * 3 + 1); g2 = __ldg(a.gt + s * 3 + 2); }
 
       // ---------------- P0: h0 = lrelu(m0 + b), a0 = sin(w0 (w tau + b)) h0 ----------------
@@ -623,6 +624,8 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fused_kernel(const FusedArgs
         if (a.dout != nullptr) {
           d0 = __ldg(a.dout + s * 3) * gs; d1 = __ldg(a.dout + s * 3 + 1) * gs; d2 = __ldg(a.dout + s * 3 + 2) * gs;
         } else {
+          // (pins the conversions here: the compiler otherwise hoists them up to the loads and stalls there for the HBM latency)
+          asm volatile("" : "+r"(g0), "+r"(g1), "+r"(g2));
           const float e0 = rgb0 - (static_cast<float>(g0) - 127.5f) / 127.5f;
           const float e1 = rgb1 - (static_cast<float>(g1) - 127.5f) / 127.5f;
           const float e2 = rgb2 - (static_cast<float>(g2) - 127.5f) / 127.5f;

@@ -178,20 +178,42 @@ def encode_latent(desc: _lib.NvpDesc, params: Sequence[torch.Tensor], coords: to
 
 class NvpFunction(torch.autograd.Function):
     """rgb = NVP.forward(coords, tsteps; params) with the reference's autograd contract
-    (gradients for the 18 parameter tensors, none for the inputs — SURVEY.md 3.3)."""
+    (gradients for the 18 parameter tensors, none for the inputs — SURVEY.md 3.3).
+
+    direct=True (the module's default, NVP.direct_grad_accumulation): backward adds each parameter's gradient straight into
+    its `.grad` (created zero-filled when missing) and returns None for it, which is what `loss.backward()` would end up
+    with -- without 18 temporary tensors (543 MB for config S), their clearing and autograd's second accumulation pass.
+    Set the module flag to False when gradients must be RETURNED (torch.autograd.grad, hooks, higher-order use)."""
 
     @staticmethod
-    def forward(ctx, desc, mode, coords, tsteps, *params):
-        ctx.desc, ctx.mode = desc, mode
+    def forward(ctx, desc, mode, direct, coords, tsteps, *params):
+        ctx.desc, ctx.mode, ctx.direct = desc, mode, direct
+        ctx.params = params if direct else None          # the leaf Parameters themselves (their .grad is the target)
         ctx.save_for_backward(coords, tsteps, *params)
         return forward(desc, params, coords, tsteps, mode)
 
     @staticmethod
     def backward(ctx, dout):
         coords, tsteps, *params = ctx.saved_tensors
-        grads = [torch.zeros_like(p) if ctx.needs_input_grad[4 + i] else None for i, p in enumerate(params)]
+        needs = ctx.needs_input_grad[5:]
+        if ctx.direct:
+            grads = []
+            for p, need in zip(ctx.params, needs):
+                if not need:
+                    grads.append(None)
+                    continue
+                g = p.grad
+                if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape or g.device != p.device:
+                    new = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    if g is not None:
+                        new.copy_(g)
+                    p.grad = g = new
+                grads.append(g)
+            backward(ctx.desc, params, grads, coords, tsteps, dout.reshape(-1, 3), ctx.mode)
+            return (None, None, None, None, None) + (None,) * len(params)
+        grads = [torch.zeros_like(p) if need else None for p, need in zip(params, needs)]
         backward(ctx.desc, params, grads, coords, tsteps, dout.reshape(-1, 3), ctx.mode)
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 def scatter_latent(desc: _lib.NvpDesc, grads: Sequence[Optional[torch.Tensor]], coords: torch.Tensor, dz: torch.Tensor) -> None:

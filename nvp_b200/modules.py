@@ -31,6 +31,9 @@ class NVP(nn.Module):
         if out_features != 3:
             raise NotImplementedError("the fused path is built for RGB output (out_features=3)")
         self.encoding_config = encoding_config
+        # model(x) -> loss.backward(): gradients are added straight into .grad (functional.NvpFunction); set to False when
+        # they must be returned instead (torch.autograd.grad, tensor hooks)
+        self.direct_grad_accumulation = True
         self.desc = _lib.make_desc(encoding_config)
         self.mode_name = mode or DEFAULT_MODE
         if self.mode_name not in _lib.MODES:
@@ -83,7 +86,8 @@ class NVP(nn.Module):
                 out = functional.forward(self.desc, self.hot_path_parameters(), coords, tsteps,
                                          self.mode | _lib.FLAG_TEMPORAL_INTERP)
             return {"model_out": out.reshape(b, t, 3)}
-        out = functional.NvpFunction.apply(self.desc, self.mode, coords, tsteps, *self.hot_path_parameters())
+        out = functional.NvpFunction.apply(self.desc, self.mode, self.direct_grad_accumulation and torch.is_grad_enabled(),
+                                           coords, tsteps, *self.hot_path_parameters())
         return {"model_out": out.reshape(b, t, 3)}
 
     def encode(self, all_coords: torch.Tensor) -> torch.Tensor:

@@ -1,7 +1,7 @@
 # Timing-only ablations of the fused MLP kernel (NVP_ABL bits, see mlp_fused.cuh).
 #   bash scripts/fused_ablate.sh build     (here: builds abl_build/libnvp_b200_ablN.so for every variant)
 #   bash scripts/fused_ablate.sh run TAG   (through gpurun: per-kind times of every variant -> gpurun_out/TAG_ablate.log)
-VARIANTS="0 1 2 4 8 16 32 3 7 15 63"
+VARIANTS=${VARIANTS:-"0 1 2 4 8 16 32 3 7 15 63"}
 NVCC=/usr/local/cuda/bin/nvcc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
 if [ "$1" = build ]; then

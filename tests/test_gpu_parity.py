@@ -280,3 +280,22 @@ def test_standalone_encoding_and_sparse_grid_operators(F):
     (so * w2.cuda()).sum().backward()
     (sr * w2.double()).sum().backward()
     assert rel_err(sg.embeddings.grad.cpu(), er.grad) <= 2e-5
+
+
+def test_autograd_grad_returns_gradients_when_direct_accumulation_is_off():
+    """NVP.direct_grad_accumulation=False: gradients are returned through autograd (torch.autograd.grad), .grad untouched;
+    they equal what the default path accumulates into .grad, and a second backward accumulates on top."""
+    g, cfg = load_golden("s_trained")
+    p = golden_params(g, cfg)
+    x = {"all_coords": dev(torch.from_numpy(g["coords"]))[None], "temporal_steps": dev(torch.from_numpy(g["tsteps"]))[None]}
+    gt = (dev(torch.from_numpy(g["gt"])).float() - 127.5) / 127.5
+    a = make_model(cfg, p, mode="fp32")
+    for _ in range(2):
+        ((a(x)["model_out"] - gt[None]) ** 2).mean().backward()
+    b = make_model(cfg, p, mode="fp32")
+    b.direct_grad_accumulation = False
+    params = [q for q in b.parameters()]
+    grads = torch.autograd.grad(((b(x)["model_out"] - gt[None]) ** 2).mean(), params)
+    assert all(q.grad is None for q in params)
+    for (k, q), gb in zip(a.named_parameters(), grads):
+        assert rel_err(q.grad.cpu(), 2 * gb.cpu()) <= 1e-5, k
