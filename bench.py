@@ -213,7 +213,8 @@ def bench_config(args, mode):
                         " + NCCL all-reduce of keyframe+MLP gradients (sparse 3-D grid owned per rank by t-slab, samples "
                         "stratified by slab)") + (", grid piece overlapped with wgrad" if getattr(args, "overlap", False) else "")
                        if args.gpus > 1 else ""),
-            "l2": "working set >> L2 (543 MB params + 543 MB grads + 4.6 GB activation tiles per step); 8 rotating input batches",
+            "l2": f"working set >> L2 ({'543' if args.config == 's' else '1086'} MB params, as much again in gradients, and GBs of "
+                  "activation tiles per step); 8 rotating input batches",
             "parallelism": f"dp{args.gpus}"}
 
 
@@ -348,6 +349,13 @@ def run_ours(args):
             i += 1
 
     pf_box = [None]
+    # the step's result (the loss sum, 4 bytes) is read back EVERY step through a pinned host buffer: the copy is
+    # enqueued behind the step and the host looks at it one step later, while the next step is already running -- the
+    # read of every step's loss is inside the timed region (the last one at its end), without the per-step stall of a
+    # synchronous .item().  --e2e-sync-loss restores the reference's `.item()` (training.py:78).
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    seen = []
 
     def e2e_step(i):
         if pf_box[0] is None:
@@ -355,13 +363,35 @@ def run_ours(args):
         batch = next(pf_box[0])
         step(*batch)
         pf_box[0].release()
-        _ = loss_sum.item()          # D2H read of the step's result
+        if args.e2e_sync_loss:
+            seen.append(loss_sum.item())
+            return
+        k = i & 1
+        loss_host[k:k + 1].copy_(loss_sum, non_blocking=True)      # D2H read of this step's result ...
+        loss_ev[k].record()
+        if i > 0:
+            loss_ev[k ^ 1].synchronize()                            # ... consumed by the host one step later
+            seen.append(float(loss_host[k ^ 1]))
+
+    def e2e_drain(k_steps):
+        if not args.e2e_sync_loss and k_steps > 0:
+            loss_ev[(k_steps - 1) & 1].synchronize()
+            seen.append(float(loss_host[(k_steps - 1) & 1]))
 
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
+    e2e_drain(min(args.warmup, 3))
     torch.cuda.synchronize()
     pf_box[0] = None                 # the timed loop starts with nothing prefetched
-    ms_e2e = timed(e2e_step, args.steps)
+    seen.clear()
+
+    def e2e_loop(i):
+        e2e_step(i)
+        if i == args.steps - 1:
+            e2e_drain(args.steps)    # the last step's loss is read inside the timed region too
+
+    ms_e2e = timed(e2e_loop, args.steps)
+    assert len(seen) == args.steps, (len(seen), args.steps)
     # keep the clock sampler fed for at least ~1.5 s of the same loop (short --steps runs give NVML no samples)
     t_end = time.time() + max(0.0, 1.5 - (ms_total + ms_e2e) / 1e3)
     i = 0
@@ -456,7 +486,9 @@ def run_ours(args):
             "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.mode == "tc" else "f32",
             "data": "synthetic", "config": bench_config(args, "tc_f16" if args.mode == "tc" else "fp32_simt"),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(19 * n_local), "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "loss_readback": "synchronous .item() every step" if args.e2e_sync_loss else
+                                     "every step, through pinned memory, consumed one step later"},
             "with_optimizer": {"value": n_global / (ms_opt / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_opt / args.steps,
                                "what": "nvp_b200.trainer.FusedTrainer.step: the same step + fused AdamW (exact torch.optim.AdamW "
                                        "semantics, gradient clear folded in)" + (f"; each rank updates the {reduce_view.numel()} replicated "
@@ -492,6 +524,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = 1,245,184 samples per GPU; strong = the reference's 1,245,184 samples per step split over "
                          "the GPUs (same sample set as one GPU)")
+    ap.add_argument("--e2e-sync-loss", action="store_true", help="end-to-end leg: read the loss with a blocking .item() every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-allreduce", action="store_true", help="N>1: all-reduce the whole gradient (no t-slab ownership)")
     ap.add_argument("--overlap", action="store_true",
