@@ -739,21 +739,33 @@ int dispatch(bool scatter, int f2, int f3, const GridArgs& a, cudaStream_t st) {
 // Voxel-neighbourhood scatter-add of the binned path: one thread per (sample, x-row of the 3x3 neighbourhood).  The three
 // voxels of a row are contiguous in memory (y fastest), so for F3 == 2 the row's 6 floats go out as one 16-byte and
 // one 8-byte reduction (2 instead of 3 lane-level reductions).  idx = 3 * sample + row.
+// Split into the loads (coordinates, the row's three gradient values as raw bits) and the reductions, so that a caller
+// can put the loads of several rows in flight before the first reduction (the compiler does not move loads across them).
+template <int F3> struct SparseRowIn { float t, x, y; RawHalfs<F3> q[3]; };
 template <int F3>
-__device__ __forceinline__ void sparse_scatter_row(const GridArgs& a, int col0, float scale, int64_t idx) {
+__device__ __forceinline__ SparseRowIn<F3> sparse_row_load(const GridArgs& a, int col0, int64_t idx) {
   const int64_t s = idx / 3;
   const int i = static_cast<int>(idx - s * 3);   // row offset + 1
-  const float t = __ldg(a.coords + 3 * s), x = __ldg(a.coords + 3 * s + 1), y = __ldg(a.coords + 3 * s + 2);
-  const int vt = nearest_voxel(t, a.tres), vx = nearest_voxel(x, a.xres), vy = nearest_voxel(y, a.yres);
-  const int cx = min(max(vx + i - 1, 0), a.xres - 1);
+  SparseRowIn<F3> in;
+  in.t = __ldg(a.coords + 3 * s); in.x = __ldg(a.coords + 3 * s + 1); in.y = __ldg(a.coords + 3 * s + 2);
   const uint8_t* tb = a.dz16t + (s >> 7) * a.kz * tc::kPanelBytes;
   const int r = static_cast<int>(s & 127);
-  float d[3][F3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int c = col0 + (i * 3 + j) * F3;
-    RawHalfs<F3> q = ld_halfs_raw<F3>(tb + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63));
-    cvt_halfs<F3>(q, d[j]);
+    in.q[j] = ld_halfs_raw<F3>(tb + (c >> 6) * tc::kPanelBytes + tc::panel_offset(r, c & 63));
+  }
+  return in;
+}
+template <int F3>
+__device__ __forceinline__ void sparse_row_commit(const GridArgs& a, float scale, int64_t idx, const SparseRowIn<F3>& in) {
+  const int i = static_cast<int>(idx % 3);
+  const int vt = nearest_voxel(in.t, a.tres), vx = nearest_voxel(in.x, a.xres), vy = nearest_voxel(in.y, a.yres);
+  const int cx = min(max(vx + i - 1, 0), a.xres - 1);
+  float d[3][F3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    cvt_halfs<F3>(in.q[j], d[j]);
 #pragma unroll
     for (int f = 0; f < F3; ++f) d[j][f] *= scale;
   }
@@ -774,6 +786,10 @@ __device__ __forceinline__ void sparse_scatter_row(const GridArgs& a, int col0, 
       red_feat<F3>(row + static_cast<size_t>(cy) * F3, d[j]);
     }
   }
+}
+template <int F3>
+__device__ __forceinline__ void sparse_scatter_row(const GridArgs& a, int col0, float scale, int64_t idx) {
+  sparse_row_commit<F3>(a, scale, idx, sparse_row_load<F3>(a, col0, idx));
 }
 
 template <int F3>
@@ -836,11 +852,51 @@ bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl, b
     if (warps >= want_warps || forced_tb || tb == 128) break;
   }
   if (warps < 1) return false;
-  // measured on config S (B200): gather 20 window + 4 voxel warps, scatter-add 22 + 2
+  // measured on config S (B200): gather 20 window + 4 voxel warps; scatter-add 16 interleaved windows + 2 (22 + 2 packed)
   int sp_warps = (d->sparse_features == F2 && F2 <= 4) ? env_int(scatter ? "NVP_BIN_SPARSE_WARPS_S" : "NVP_BIN_SPARSE_WARPS_G", scatter ? 2 : 4) : 0;
   sp_warps = std::max(0, std::min(sp_warps, kBinThreadsMax / 32 - 1));
+  // (the shared-memory limit of the scatter-add's layout is applied below)
   warps = std::max(1, std::min(std::min(warps, kBinThreadsMax / 32 - sp_warps),
                                env_int(scatter ? "NVP_BIN_WARPS_S" : "NVP_BIN_WARPS_G", scatter ? 22 : 20)));
+  size_t region_floats = static_cast<size_t>((bt.base[L] * F2 + 3) & ~3), table_bytes = 0;
+  if (scatter) {
+    // the scatter-add stages the samples' latent-gradient slices (NC 16-byte chunks each) in a 2 x 32-sample ring per warp
+    constexpr size_t kScatterBudget = 226 * 1024;   // all of an SM's shared memory but the kernel's static tables
+    const int NC = L * F2 / 8;
+    const size_t ring_floats = 2 * 32 * static_cast<size_t>(NC) * 4;
+    const size_t idle_floats = (L % 16 != 0) ? 32 * 2 * static_cast<size_t>(F2) : 0;
+    bt.dz_extra_floats = static_cast<int32_t>(ring_floats + idle_floats);
+    bt.dz_base = static_cast<int32_t>(region_floats + stage_floats(scatter));
+    bt.idle_base = static_cast<int32_t>(region_floats + stage_floats(scatter) + ring_floats);
+    bt.dz_stride = NC * 16;
+    const int cap = warps;
+    warps = std::min(cap, static_cast<int>(kScatterBudget / ((region_floats + stage_floats(scatter) + ring_floats + idle_floats) * sizeof(float))));
+    if (warps < 1) return false;
+    if (F2 == 2 && L == 16 && env_int("NVP_BIN_ILV", 1) != 0) {   // (16 levels: every lane has a level)
+      // bank-interleaved windows (grid_binned.cuh): region rows = the largest window of each level group.  The ring lives
+      // in the rows of group 1 that the group's first NC levels (whose bank pairs cover NC * 16 bytes of a row) leave unused.
+      int rows[2] = {0, 0}, emax = 0, ring_row0 = 0;
+      for (int l = 0; l < L; ++l) {
+        const int slots = (bt.E[l] + 1) / 2 * bt.E[l];
+        rows[l >> 3] = std::max(rows[l >> 3], slots);
+        if (l >= 8 && l < 8 + NC) ring_row0 = std::max(ring_row0, slots);
+        emax = std::max(emax, bt.E[l]);
+      }
+      const size_t ilv_floats = static_cast<size_t>(rows[0] + rows[1]) * 32;
+      const bool ring_inside = rows[1] - ring_row0 >= 64;
+      const size_t per_warp = (ilv_floats + stage_floats(scatter) + (ring_inside ? 0 : ring_floats)) * sizeof(float);   // no idle lanes
+      const int ilv_warps = static_cast<int>((kScatterBudget - bt.base[L] * sizeof(uint32_t)) / per_warp);
+      if (ilv_warps >= env_int("NVP_BIN_ILV_MIN_WARPS", 14) && ilv_floats <= (1u << 14) && emax < 64) {
+        bt.ilv = 1; bt.ilv_rows[0] = rows[0]; bt.ilv_rows[1] = rows[1];
+        region_floats = ilv_floats;
+        table_bytes = bt.base[L] * sizeof(uint32_t);
+        warps = std::min(cap, std::min(ilv_warps, env_int("NVP_BIN_WARPS_ILV", 32)));
+        bt.dz_base = static_cast<int32_t>(ring_inside ? (rows[0] + ring_row0) * 32 : ilv_floats + stage_floats(scatter));
+        bt.dz_stride = ring_inside ? 128 : NC * 16;
+        bt.dz_extra_floats = ring_inside ? 0 : static_cast<int32_t>(ring_floats);
+      }
+    }
+  }
   const int64_t avg = (n + bt.nt - 1) / bt.nt;
   int chunk = env_int("NVP_BIN_CHUNK", 0);
   if (chunk <= 0) chunk = static_cast<int>(std::min<int64_t>(1 << 20, std::max<int64_t>(128, 2 * avg)));
@@ -848,7 +904,7 @@ bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl, b
   pl->bt = bt;
   pl->warps = warps;
   pl->sp_warps = sp_warps;
-  pl->smem = static_cast<size_t>(warps) * (static_cast<size_t>((bt.base[L] * F2 + 3) & ~3) + kStageFloats) * sizeof(float);
+  pl->smem = static_cast<size_t>(warps) * (region_floats + stage_floats(scatter) + bt.dz_extra_floats) * sizeof(float) + table_bytes;
   pl->max_tasks = static_cast<int>(3 * static_cast<int64_t>(bt.nt) + 3 * n / bt.chunk + 8);
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -882,19 +938,26 @@ int device_sms() {
   return sms;
 }
 
-template <int F2, bool SCATTER, int THREADS>
+template <int F2, bool SCATTER, int THREADS, bool ILV = false>
 int launch_binned_variant(const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
-  NVP_CUDA(cudaFuncSetAttribute(grid_binned_kernel<F2, SCATTER, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  NVP_CUDA(cudaFuncSetAttribute(grid_binned_kernel<F2, SCATTER, THREADS, ILV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(pl.smem)));
   const int blocks = a.sp_warps > 0 ? device_sms()
                                     : std::max(1, std::min(device_sms(), (pl.max_tasks + pl.warps - 1) / pl.warps));
-  grid_binned_kernel<F2, SCATTER, THREADS><<<blocks, (pl.warps + a.sp_warps) * 32, pl.smem, st>>>(a);
+  grid_binned_kernel<F2, SCATTER, THREADS, ILV><<<blocks, (pl.warps + a.sp_warps) * 32, pl.smem, st>>>(a);
   return 0;
 }
 template <int F2, bool SCATTER>
 int launch_binned_kernel(const BinPlan& pl, const BinArgs& a, cudaStream_t st) {
   // the register budget of a variant follows from its thread bound (64 K registers per SM)
   const int warps = pl.warps + a.sp_warps;
+  if constexpr (SCATTER && F2 == 2) {
+    if (a.bt.ilv) {
+      if (warps <= 16) return launch_binned_variant<F2, SCATTER, 512, true>(pl, a, st);
+      if (warps <= 18) return launch_binned_variant<F2, SCATTER, 576, true>(pl, a, st);
+      return launch_binned_variant<F2, SCATTER, 768, true>(pl, a, st);
+    }
+  }
   if (warps <= 16) return launch_binned_variant<F2, SCATTER, 512>(pl, a, st);
   if (warps <= 24) return launch_binned_variant<F2, SCATTER, 768>(pl, a, st);
   return launch_binned_variant<F2, SCATTER, 1024>(pl, a, st);

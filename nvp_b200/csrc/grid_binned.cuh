@@ -12,10 +12,13 @@
 //   gather : the window is copied from the plane table with cp.async (rows coalesced, all cells in flight together);
 //            then lane = sample: every lane walks the levels, reads its 4 corners from the window and writes its slice
 //            of the latent row as whole 16-byte chunks - same corner order and fma chain as the direct kernel;
-//   scatter: lane = (level, cell row): the region starts at zero, the warp takes one sample per step and every lane does
-//            a plain (non-atomic) read-modify-write of two adjacent corners - lanes of one sample never collide
-//            (different levels / rows), consecutive samples are ordered by __syncwarp - and the region is flushed once
-//            per task with one vector reduction per non-zero cell: ~8 global reductions per (sample, plane), not 64.
+//   scatter: lane = (level, row parity): the region starts at zero and the warp takes one sample per step.  Of the
+//            sample's two window rows each level's lane pair takes the one of its own parity, so a window cell is only
+//            ever touched by ONE lane: plain (non-atomic) read-modify-writes of two adjacent corners, ordered by program
+//            order alone - no synchronisation between samples, no branch in the loop.  The samples' latent gradients are
+//            staged in shared memory by cp.async one batch (32 samples) ahead.  The region is flushed once per task with
+//            one vector reduction per non-zero cell: ~8 global reductions per (sample, plane), not 64.  With 8-byte
+//            cells and 16 levels the region is bank-interleaved (see grid_binned_kernel): no bank conflicts at all.
 // Cell addressing keeps the reference's edge behaviour (flat index without clamping, then modulo the level size,
 // SURVEY.md A.2): the window stores the "virtual" cells (res, j) / (i, res) and maps them to their aliases on load /
 // flush.  Samples whose cells fall outside the window (coordinates outside [0,1]) take the direct global path.
@@ -30,6 +33,14 @@ struct BinTab {
   uint32_t magic[NVP_MAX_LEVELS];    // idx / E == (idx * magic) >> 20 for idx < E * E
   int32_t tb, log_tb, nt;            // tiles per axis (power of two), log2, tb * tb
   int32_t chunk;                     // samples per task
+  // scatter-add with 8-byte cells only: bank-interleaved window layout (see grid_binned_kernel); 0 = packed layout
+  int32_t ilv;
+  int32_t ilv_rows[2];               // 128-byte region rows of level group 0 (levels 0-7) and 1 (levels 8-15)
+  // scatter-add: staging ring of the samples' latent-gradient slices (2 batches of 32 samples, filled by cp.async)
+  int32_t dz_extra_floats;           // per-warp floats behind the batch stage (0: the ring lives in unused region rows)
+  int32_t dz_base;                   // float offset of the ring from the warp's region
+  int32_t dz_stride;                 // bytes from one sample's slice to the next
+  int32_t idle_base;                 // float offset of 32 private cell pairs for lanes without a level (n_levels % 16 != 0)
 };
 
 struct BinArgs {
@@ -60,6 +71,9 @@ struct BinArgs {
   int win_warps, sp_warps;
 };
 
+#ifndef NVP_SP_UNROLL
+#define NVP_SP_UNROLL 4   // rows in flight per thread of the voxel role's scatter-add
+#endif
 constexpr int kBinThreadsMax = 1024;   // kernel variants are compiled for 512 / 768 / 1024 threads per CTA
 
 // One bucket entry: byte offset of the sample's latent row inside the tile buffer (0xffffffff = padding entry of a
@@ -69,7 +83,8 @@ struct __align__(16) StagedSample { uint32_t rowoff, swz; float u0, u1; };
 // table (n_levels <= 32 x 32 B).
 struct __align__(16) LevelWindow { float scale; int lo0, lo1, base; int E, amax0, amax1, res; };
 constexpr int kStageFloats = NVP_MAX_LEVELS * sizeof(LevelWindow) / sizeof(float);
-static_assert(kStageFloats * sizeof(float) >= 32 * sizeof(StagedSample), "stage too small");
+constexpr int kScatterStageFloats = 32 * sizeof(StagedSample) / sizeof(float);   // the scatter-add needs the batch only
+__host__ __device__ constexpr int stage_floats(bool scatter) { return scatter ? kScatterStageFloats : kStageFloats; }
 
 __device__ __forceinline__ int bin_tile_axis(float u, int tb) {
   const int b = __float2int_rz(u * static_cast<float>(tb));   // tb is a power of two: the product is exact
@@ -187,6 +202,34 @@ __device__ __forceinline__ void sts_feat(float* p, const float (&v)[F]) {
   }
 }
 
+// The same through a 32-bit shared-window address (keeps the address arithmetic of the scatter-add's hot loop to one add).
+template <int F>
+__device__ __forceinline__ void lds_feat_s(uint32_t addr, float (&v)[F]) {
+  if constexpr (F == 1) {
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr) : "memory");
+  } else if constexpr (F == 2) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < F; i += 4)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i]), "=f"(v[i + 1]), "=f"(v[i + 2]), "=f"(v[i + 3])
+                   : "r"(addr + i * 4) : "memory");
+  }
+}
+template <int F>
+__device__ __forceinline__ void sts_feat_s(uint32_t addr, const float (&v)[F]) {
+  if constexpr (F == 1) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v[0]) : "memory");
+  } else if constexpr (F == 2) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v[0]), "f"(v[1]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < F; i += 4)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + i * 4), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
+                   "f"(v[i + 3]) : "memory");
+  }
+}
+
 // Rare path (plane coordinates outside [0,1], i.e. cells outside the task's window): the direct global access of the
 // unbinned kernels.  Out of line to keep the hot loops small.
 template <int F2> struct CornerPair { float a[F2], b[F2]; };
@@ -256,9 +299,22 @@ __device__ __forceinline__ void region_io(float* __restrict__ reg, const float* 
   }
 }
 
-template <int F2, bool SCATTER, int THREADS>
+// Interleaved window layout of the scatter-add (ILV; 8-byte cells, 16 levels).  In the packed layout a lane's cell sits
+// at an arbitrary bank and the 32 lanes of a sample's read-modify-write collide (measured on config S: 103 M shared
+// wavefronts per step, 54 M of them bank conflicts).  Here every (level, row parity) pair - i.e. every lane - owns one fixed
+// 8-byte bank pair: a 128-byte region row holds slot s of the 16 pairs of one level group (levels 0-7 | 8-15), and the
+// window cell (aa, row) of level l lives in slot (row >> 1) * E_l + aa of pair (l & 7, row & 1).  The 16 lanes of a
+// half-warp always hit 16 different bank pairs: every 64-bit access is conflict-free (57 M wavefronts, 5 M conflicts, all
+// in the flush).  The price is a region as tall as the largest window of each group (13.25 KiB instead of 5 KiB for config
+// S: 16 windows per SM instead of 22); the rows that the group's small levels leave unused hold the gradient staging ring,
+// and the flush walks a per-CTA table of the populated (slot, pair) entries instead of the windows.
+constexpr int kIlvOffBits = 14, kIlvLevelBits = 4, kIlvCoordBits = 6;
+
+template <int F2, bool SCATTER, int THREADS, bool ILV = false>
 __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a) {
+  static_assert(!ILV || (SCATTER && F2 == 2), "the interleaved layout is the scatter-add's, for 8-byte cells");
   extern __shared__ __align__(16) float s_region[];
+  __shared__ int s_nitems;
   __shared__ float s_scale[NVP_MAX_LEVELS];
   __shared__ int s_res[NVP_MAX_LEVELS], s_off[NVP_MAX_LEVELS], s_E[NVP_MAX_LEVELS], s_base[NVP_MAX_LEVELS + 1];
   __shared__ uint32_t s_magic[NVP_MAX_LEVELS];
@@ -274,6 +330,33 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = a.win_warps;
+  const int region_floats = ILV ? (a.bt.ilv_rows[0] + a.bt.ilv_rows[1]) * 32 : (a.bt.base[L] * F2 + 3) & ~3;
+  const int warp_floats = region_floats + stage_floats(SCATTER) + (SCATTER ? a.bt.dz_extra_floats : 0);
+  uint32_t* s_items = reinterpret_cast<uint32_t*>(s_region + static_cast<size_t>(nwarps) * warp_floats);
+  if constexpr (ILV) {
+    if (warp == 0) {   // flush table: the populated entries of a region, row-major (consecutive entries = different banks)
+      const int rows0 = a.bt.ilv_rows[0], rows = rows0 + a.bt.ilv_rows[1];
+      int n = 0;
+      for (int c0 = 0; c0 < rows * 16; c0 += 32) {
+        const int c = c0 + lane, row = c >> 4, p = c & 15;
+        const int g = row >= rows0 ? 1 : 0, slot = row - (g ? rows0 : 0), l = g * 8 + (p >> 1);
+        bool valid = false;
+        uint32_t e = 0;
+        if (row < rows && l < L) {
+          const int E = s_E[l], q = slot / E, aa = slot - q * E, wrow = 2 * q + (p & 1);
+          valid = wrow < E;
+          e = static_cast<uint32_t>(row * 32 + p * 2) | static_cast<uint32_t>(l) << kIlvOffBits |
+              static_cast<uint32_t>(aa) << (kIlvOffBits + kIlvLevelBits) |
+              static_cast<uint32_t>(wrow) << (kIlvOffBits + kIlvLevelBits + kIlvCoordBits);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) s_items[n + __popc(m & ((1u << lane) - 1u))] = e;
+        n += __popc(m);
+      }
+      if (lane == 0) s_nitems = n;
+    }
+    __syncthreads();
+  }
   if (warp >= nwarps) {
     if constexpr (F2 <= 4) {   // (the role is only enabled when the 3-D grid has F2 features per voxel)
       const int64_t gtid = (static_cast<int64_t>(blockIdx.x) * a.sp_warps + (warp - nwarps)) * 32 + lane;
@@ -281,8 +364,18 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
       if constexpr (SCATTER) {
         if (a.sp.gsparse != nullptr) {
           const float sscale = a.sp.scale_ptr ? a.sp.scale * __ldg(a.sp.scale_ptr) : a.sp.scale;
-#pragma unroll 2
-          for (int64_t idx = gtid; idx < 3 * a.sp.n; idx += gstride) sparse_scatter_row<F2>(a.sp, a.sp_col0, sscale, idx);
+          // four rows' loads in flight per thread before their reductions (few warps run this role: latency-bound)
+          constexpr int U = NVP_SP_UNROLL;
+          const int64_t total = 3 * a.sp.n;
+          int64_t idx = gtid;
+          for (; idx + (U - 1) * gstride < total; idx += U * gstride) {
+            SparseRowIn<F2> in[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) in[u] = sparse_row_load<F2>(a.sp, a.sp_col0, idx + u * gstride);
+#pragma unroll
+            for (int u = 0; u < U; ++u) sparse_row_commit<F2>(a.sp, sscale, idx + u * gstride, in[u]);
+          }
+          for (; idx < total; idx += gstride) sparse_scatter_row<F2>(a.sp, a.sp_col0, sscale, idx);
         }
       } else {
 #pragma unroll 2
@@ -291,15 +384,14 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
     }
     return;
   }
-  const int region_floats = (a.bt.base[L] * F2 + 3) & ~3;
-  float* reg = s_region + static_cast<size_t>(warp) * (region_floats + kStageFloats);
+  float* reg = s_region + static_cast<size_t>(warp) * warp_floats;
   StagedSample* stage = reinterpret_cast<StagedSample*>(reg + region_floats);
   const int n_tasks = __ldg(a.n_tasks);
   const float inv_tb = 1.0f / static_cast<float>(a.bt.tb);
   const int pw = L * F2;
   float scale = 1.0f;
   if constexpr (SCATTER) scale = a.scale_ptr ? a.scale * __ldg(a.scale_ptr) : a.scale;
-  const int c1 = lane & 1;
+  const int par = lane & 1;   // scatter-add: the window-row parity this lane owns
 
   for (int task = blockIdx.x * nwarps + warp; task < n_tasks; task += gridDim.x * nwarps) {
     const int2 tk = __ldg(a.tasks + task);
@@ -386,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
       }
       __syncwarp();   // the level table and the window are rewritten by the next task
     } else for (int lb = 0; lb < L; lb += 16) {
-      // ---- scatter-add: lane = (level, cell row); one sample per step of the warp
+      // ---- scatter-add: lane = (level, row parity); one sample per step of the warp
       const int le = min(L, lb + 16);
       const bool lv = lb + (lane >> 1) < L;
       const int l = lv ? lb + (lane >> 1) : L - 1;
@@ -396,88 +488,143 @@ __global__ void __launch_bounds__(THREADS, 1) grid_binned_kernel(const BinArgs a
       const size_t goff = static_cast<size_t>(s_off[l]);
       const int lo0 = static_cast<int>(floorf(fmaf(sc, ub0, 0.5f))), lo1 = static_cast<int>(floorf(fmaf(sc, ub1, 0.5f)));
       const unsigned amax0 = static_cast<unsigned>(min(E - 2, res - 1 - lo0)), amax1 = static_cast<unsigned>(min(E - 2, res - 1 - lo1));
-      float* rl = reg + (static_cast<size_t>(s_base[l]) + c1 * E) * F2;
-      const int col = plane * pw + l * F2;
-      uint8_t* zb = a.z16t + static_cast<size_t>(col >> 6) * tc::kPanelBytes + ((col & 7) << 1);
-      const uint32_t cc16 = static_cast<uint32_t>((col & 63) >> 3) << 4;
+      // Row ownership: of a sample's two window rows bb, bb + 1 the lane takes the one whose parity is its own.  A window
+      // cell is then only ever touched by one lane, so consecutive samples need no ordering between lanes: each lane's
+      // read-modify-writes are ordered by program order alone.
+      // This lane's window base: packed = the level's window; interleaved = the bank pair of (level, parity).
+      float* rl = ILV ? reg + ((lane >> 4) ? a.bt.ilv_rows[0] * 32 : 0) + (((lane >> 1) & 7) << 2) + (par << 1)
+                      : reg + static_cast<size_t>(s_base[l]) * F2;
+      constexpr int kNextCorner = ILV ? 32 : F2;   // floats from the cell (aa, row) to (aa + 1, row)
+      // The samples' latent gradients (this plane's slice of the row: NC 16-byte chunks) are staged in shared memory one
+      // batch ahead by cp.async: the copies of batch i + 1 are in flight while batch i is processed, so the warp never
+      // waits for them (in registers only 16 samples could be kept in flight, and the kernel was bound by that latency).
+      const int NC = pw >> 3, chunk0 = plane * NC;
+      const uint32_t nc_magic = 65536u / static_cast<uint32_t>(NC) + 1u;   // idx / NC for idx < 32 * NC <= 512
+      uint8_t* dzs = reinterpret_cast<uint8_t*>(reg + a.bt.dz_base);
+      const uint32_t dz_stride = static_cast<uint32_t>(a.bt.dz_stride), dz_buf = 32u * dz_stride;
+      const uint8_t* my_dz = dzs + l * F2 * 2;   // this lane's level inside a staged slice
+      auto issue_dz = [&](const uint4& r, uint32_t buf) {   // r = this lane's record of that batch (lane = sample)
+        for (int idx = lane; idx < 32 * NC; idx += 32) {
+          const int smp = static_cast<int>((static_cast<uint32_t>(idx) * nc_magic) >> 16), q = idx - smp * NC;
+          const uint32_t rowoff = __shfl_sync(0xffffffffu, r.x, smp), swz = __shfl_sync(0xffffffffu, r.y, smp);
+          const int c = chunk0 + q;
+          const bool real = rowoff != 0xffffffffu;
+          const uint8_t* src = real ? a.z16t + static_cast<size_t>(c >> 3) * tc::kPanelBytes + rowoff +
+                                          ((static_cast<uint32_t>(c & 7) << 4) ^ swz)
+                                    : zero_src;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dzs + buf * dz_buf + smp * dz_stride + q * 16)),
+                       "l"(src), "r"(real ? 16u : 0u) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
 
       uint4 rec = beg + lane < end ? __ldg(recs + beg + lane) : pad_rec;
+      uint4 rec_next = beg + 32 + lane < end ? __ldg(recs + beg + 32 + lane) : pad_rec;
       {
         float4* r4 = reinterpret_cast<float4*>(reg);
         for (int i = lane; i < region_floats / 4; i += 32) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncwarp();
+      issue_dz(rec, 0u);
 
-      // one sample: window-relative cell of the lane's level, the two corners of the lane's row and their weights
-      auto geometry = [&](const StagedSample& q, float& ka, float& kb, int& i0, int& i1, int& loc) -> bool {
+      // One sample, prepared ahead of its turn: byte offset of the lane's first corner from its window base, the two
+      // corner weights and the gradient bits.  The hot loop has no branch: a sample outside the window (coordinates outside
+      // [0,1] - rare) and an idle lane (level >= L) add zero to a cell that only this lane touches, and the batch is
+      // revisited afterwards by the direct path if any lane saw an outside sample.
+      constexpr uint32_t kNextCornerBytes = kNextCorner * 4;
+      const uint32_t rl_s = lv ? tc::smem_u32(rl) : tc::smem_u32(reg + a.bt.idle_base + lane * (2 * F2));
+      const int own_loc = lv ? (ILV ? 0 : par * E * F2 * 4) : 0;   // cell (0, parity row): owned by this lane
+      bool saw_outside = false;
+      struct Prepared { float ka, kb; int loc; RawHalfs<F2> d; };
+      auto prepare = [&](int j, uint32_t buf) -> Prepared {
+        const StagedSample q = stage[j];
+        Prepared g;
         const float p0 = fmaf(sc, q.u0, 0.5f), p1 = fmaf(sc, q.u1, 0.5f);
         const float f0 = floorf(p0), f1 = floorf(p1);
-        i0 = static_cast<int>(f0); i1 = static_cast<int>(f1);
         const float w0 = p0 - f0, w1 = p1 - f1;
+        const int aa = static_cast<int>(f0) - lo0, bb = static_cast<int>(f1) - lo1;
+        const int c1 = (bb ^ par) & 1, wrow = bb + c1;     // the lane's row of this sample
         const float wr = c1 ? w1 : 1.0f - w1;
-        ka = (1.0f - w0) * wr; kb = w0 * wr;
-        const int aa = i0 - lo0, bb = i1 - lo1;
-        loc = (bb * E + aa) * F2;
-        return static_cast<unsigned>(aa) <= amax0 && static_cast<unsigned>(bb) <= amax1;
+        g.ka = (1.0f - w0) * wr; g.kb = w0 * wr;
+        g.loc = ILV ? ((wrow >> 1) * E + aa) << 7 : (wrow * E + aa) * (F2 * 4);
+        g.d = lds_halfs_raw<F2>(my_dz + buf * dz_buf + j * dz_stride);
+        const bool inside = static_cast<unsigned>(aa) <= amax0 && static_cast<unsigned>(bb) <= amax1;
+        saw_outside |= !inside;
+        if (!(inside && lv)) {
+          g.loc = own_loc;
+#pragma unroll
+          for (int w = 0; w < (F2 + 1) / 2; ++w) g.d.w[w] = 0u;
+        }
+        return g;
       };
 
-      for (int i = beg; i < end; i += 32) {
+      uint32_t buf = 0;
+      for (int i = beg; i < end; i += 32, buf ^= 1u) {
         reinterpret_cast<uint4*>(stage)[lane] = rec;
+        const uint4 rec_next2 = i + 64 + lane < end ? __ldg(recs + i + 64 + lane) : pad_rec;   // two batches ahead
+        if (i + 32 < end) issue_dz(rec_next, buf ^ 1u);   // (that buffer was drained by the previous batch)
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this batch's copies have landed
         __syncwarp();
-        rec = i + 32 + lane < end ? __ldg(recs + i + 32 + lane) : pad_rec;   // lands while this batch is processed
         const int cnt = min(32, end - i);
-
-        if constexpr (SCATTER) {
-          // latent-gradient values are fetched (as raw bits) one group ahead of their use: two register buffers
-          constexpr int G = F2 <= 2 ? 8 : (F2 == 4 ? 4 : 2);
-          constexpr int NG = 32 / G;
-          RawHalfs<F2> dA[G], dB[G];
-          auto load_group = [&](int g, RawHalfs<F2> (&dg)[G]) {
+        Prepared cur = prepare(0, buf);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+          const Prepared nxt = prepare(min(j + 1, 31), buf);   // independent of the read-modify-write below
+          float va[F2], vb[F2], dv[F2];
+          cvt_halfs<F2>(cur.d, dv);
+          const uint32_t addr = rl_s + static_cast<uint32_t>(cur.loc);
+          lds_feat_s<F2>(addr, va);
+          lds_feat_s<F2>(addr + kNextCornerBytes, vb);
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-              const StagedSample q = stage[g * G + j];
-              const uint8_t* src = q.rowoff != 0xffffffffu ? zb + q.rowoff + (cc16 ^ q.swz) : zero_src;
-              dg[j] = ld_halfs_raw<F2>(src);
-            }
-          };
-          auto process_group = [&](int g, const RawHalfs<F2> (&dg)[G]) {
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-              const StagedSample q = stage[g * G + j];
-              float ka, kb, va[F2], vb[F2], dv[F2];
-              int i0, i1, loc;
-              const bool inside = geometry(q, ka, kb, i0, i1, loc);
-              cvt_halfs<F2>(dg[j], dv);
-              if (lv) {
-                if (inside) {
-                  lds_feat<F2>(rl + loc, va);
-                  lds_feat<F2>(rl + loc + F2, vb);
-#pragma unroll
-                  for (int f = 0; f < F2; ++f) { va[f] = fmaf(ka, dv[f], va[f]); vb[f] = fmaf(kb, dv[f], vb[f]); }
-                  sts_feat<F2>(rl + loc, va);
-                  sts_feat<F2>(rl + loc + F2, vb);
-                } else {
-                  CornerPair<F2> cp;
-#pragma unroll
-                  for (int f = 0; f < F2; ++f) { cp.a[f] = dv[f]; cp.b[f] = 0.0f; }
-                  direct_corner_pair_add<F2>(gkp + goff * F2, i0 + (i1 + c1) * res, cells, ka * scale, kb * scale, cp);
-                }
-              }
-              __syncwarp();   // orders this sample's stores before the next sample's loads (other lanes)
-            }
-          };
-          load_group(0, dA);
-#pragma unroll 1
-          for (int g = 0; g < NG; g += 2) {
-            if (cnt > (g + 1) * G) load_group(g + 1, dB);
-            if (cnt > g * G) process_group(g, dA);
-            if (g + 2 < NG && cnt > (g + 2) * G) load_group(g + 2, dA);
-            if (cnt > (g + 1) * G) process_group(g + 1, dB);
-          }
+          for (int f = 0; f < F2; ++f) { va[f] = fmaf(cur.ka, dv[f], va[f]); vb[f] = fmaf(cur.kb, dv[f], vb[f]); }
+          sts_feat_s<F2>(addr, va);
+          sts_feat_s<F2>(addr + kNextCornerBytes, vb);
+          cur = nxt;
         }
-        __syncwarp();   // the stage is rewritten by the next batch
+        if (__any_sync(0xffffffffu, saw_outside && lv)) {
+          // direct global reductions for the samples outside this task's window
+          for (int j = 0; j < cnt; ++j) {
+            const StagedSample q = stage[j];
+            const float p0 = fmaf(sc, q.u0, 0.5f), p1 = fmaf(sc, q.u1, 0.5f);
+            const float f0 = floorf(p0), f1 = floorf(p1);
+            const int i0 = static_cast<int>(f0), i1 = static_cast<int>(f1);
+            const int aa = i0 - lo0, bb = i1 - lo1;
+            if (!lv || (static_cast<unsigned>(aa) <= amax0 && static_cast<unsigned>(bb) <= amax1)) continue;
+            const float w0 = p0 - f0, w1 = p1 - f1;
+            const int c1 = (bb ^ par) & 1;
+            const float wr = c1 ? w1 : 1.0f - w1;
+            CornerPair<F2> cp;
+            cvt_halfs<F2>(lds_halfs_raw<F2>(my_dz + buf * dz_buf + j * dz_stride), cp.a);
+#pragma unroll
+            for (int f = 0; f < F2; ++f) cp.b[f] = 0.0f;
+            direct_corner_pair_add<F2>(gkp + goff * F2, i0 + (i1 + c1) * res, cells, (1.0f - w0) * wr * scale, w0 * wr * scale, cp);
+          }
+          saw_outside = false;
+        }
+        __syncwarp();   // the stage and this staging buffer are rewritten by the following batches
+        rec = rec_next; rec_next = rec_next2;
       }
-      if constexpr (SCATTER) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if constexpr (ILV) {
+        const int n_items = s_nitems;
+        for (int it = lane; it < n_items; it += 32) {
+          const uint32_t e = s_items[it];
+          float v[F2];
+          lds_feat<F2>(reg + (e & ((1u << kIlvOffBits) - 1u)), v);
+          if (v[0] == 0.0f && v[1] == 0.0f) continue;
+          const int fl = (e >> kIlvOffBits) & ((1 << kIlvLevelBits) - 1);
+          const int aa = (e >> (kIlvOffBits + kIlvLevelBits)) & ((1 << kIlvCoordBits) - 1);
+          const int wrow = (e >> (kIlvOffBits + kIlvLevelBits + kIlvCoordBits)) & ((1 << kIlvCoordBits) - 1);
+          const float fsc = s_scale[fl];
+          const int fres = s_res[fl];
+          const int g0 = static_cast<int>(floorf(fmaf(fsc, ub0, 0.5f))) + aa, g1 = static_cast<int>(floorf(fmaf(fsc, ub1, 0.5f))) + wrow;
+          if (g0 > fres || g1 > fres) continue;   // (res, j) and (i, res) are the aliased "virtual" cells
+#pragma unroll
+          for (int f = 0; f < F2; ++f) v[f] *= scale;
+          red_feat<F2>(gkp + (static_cast<size_t>(s_off[fl]) + wrap_cell(g0 + g1 * fres, fres * fres)) * F2, v);
+        }
+      } else if constexpr (SCATTER) {
         region_io<F2, REGION_FLUSH>(reg, nullptr, gkp, s_scale, s_res, s_off, s_E, s_base, s_magic, lb, le, ub0, ub1, scale, lane);
       }
       __syncwarp();

@@ -21,6 +21,23 @@ __device__ __forceinline__ RawHalfs<F> ld_halfs_raw(const uint8_t* p) {
   }
   return q;
 }
+// the same from a shared-memory staging buffer
+template <int F>
+__device__ __forceinline__ RawHalfs<F> lds_halfs_raw(const uint8_t* p) {
+  RawHalfs<F> q;
+  if constexpr (F == 1) {
+    q.w[0] = *reinterpret_cast<const unsigned short*>(p);
+  } else if constexpr (F == 2) {
+    q.w[0] = *reinterpret_cast<const uint32_t*>(p);
+  } else if constexpr (F == 4) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    q.w[0] = t.x; q.w[1] = t.y;
+  } else {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    q.w[0] = t.x; q.w[1] = t.y; q.w[2] = t.z; q.w[3] = t.w;
+  }
+  return q;
+}
 template <int F>
 __device__ __forceinline__ void cvt_halfs(const RawHalfs<F>& q, float (&v)[F]) {
   if constexpr (F == 1) {

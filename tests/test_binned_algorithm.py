@@ -92,3 +92,34 @@ def test_binned_algorithm_equals_the_oracle_including_edges_and_out_of_range(F):
     _, grad = emulate(u, table, F, plan, dz=dz)                               # scatter-add: windows start at zero
     assert np.abs(out - ref.detach().numpy()).max() <= 1e-9
     assert np.abs(grad - params.grad.numpy()).max() <= 1e-9
+
+
+def test_interleaved_scatter_layout_is_injective_and_bank_conflict_free():
+    """The scatter-add's bank-interleaved window layout (grid_binned.cuh, ILV): cell (aa, row) of level l sits in slot
+    (row >> 1) * E_l + aa of the bank pair (l & 7, row & 1) of its level group's region rows.  Restated here from the plan:
+    distinct window cells never share an address, and the 16 lanes of a half-warp (8 levels x the two corner rows of one
+    sample) always touch 16 different 8-byte bank pairs, whatever the sample's position in its windows."""
+    L = 16
+    d = _lib.NvpDesc(2, L, 16, 1.35, 2, 6, 20, 24, 128, 3, 30.0)
+    ext = _lib.grid_bin_plan(d, 4096)["window_extent"]
+    rows = [max((E + 1) // 2 * E for E in ext[:8]), max((E + 1) // 2 * E for E in ext[8:])]
+
+    def address(l, aa, row):      # float offset inside the warp's region
+        return (rows[0] * 32 if l >= 8 else 0) + ((l & 7) << 2) + ((((row >> 1) * ext[l] + aa) << 5) + ((row & 1) << 1))
+
+    seen = set()
+    for l in range(L):
+        for row in range(ext[l]):
+            for aa in range(ext[l]):
+                a = address(l, aa, row)
+                assert a not in seen and a + 1 not in seen and a % 2 == 0 and a + 1 < (rows[0] + rows[1]) * 32
+                seen.update((a, a + 1))
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        for half in (0, 1):
+            banks = []
+            for l in range(8 * half, 8 * half + 8):
+                aa, bb = rng.integers(0, ext[l] - 1, 2)          # top-left corner; the lanes take rows bb and bb + 1
+                for c1 in (0, 1):
+                    banks.append((address(l, aa + rng.integers(0, 2), bb + c1) // 2) % 16)
+            assert len(set(banks)) == 16
