@@ -809,7 +809,7 @@ struct BinPlan {
   int sp_warps;         // extra warps per CTA running the voxel-neighbourhood role (0: separate kernels)
   size_t smem;          // dynamic shared memory per CTA
   int max_tasks;
-  size_t o_cnt, o_offs, o_cursor, o_ntasks, o_zeros, o_tasks, o_recs, total;   // workspace byte offsets
+  size_t o_cnt, o_offs, o_cursor, o_ntasks, o_zeros, o_scan, o_tasks, o_recs, total;   // workspace byte offsets
 };
 
 int env_int(const char* name, int dflt) {
@@ -830,7 +830,7 @@ bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl, b
   const int want_warps = 20;   // a tile size qualifies when this many private windows fit one SM
   BinTab bt{};
   int warps = 0;
-  for (int tb = 32; tb <= 128; tb <<= 1) {   // 3 * tb^2 counters must fit the scan kernel's shared memory
+  for (int tb = 32; tb <= 128; tb <<= 1) {   // (3 * tb^2 buckets: a multiple of the scan kernel's 1024 per CTA)
     if (forced_tb && tb != forced_tb) continue;
     int base = 0;
     for (int l = 0; l < L; ++l) {
@@ -913,6 +913,7 @@ bool plan_bins(const nvp_desc* d, const LevelTab& tab, int64_t n, BinPlan* pl, b
   pl->o_cursor = take(sizeof(int32_t) * 3 * bt.nt);
   pl->o_ntasks = take(sizeof(int32_t));
   pl->o_zeros = take(16);
+  pl->o_scan = take(sizeof(unsigned long long) * (2 + (3 * static_cast<size_t>(bt.nt) + 1023) / 1024));
   pl->o_tasks = take(sizeof(int2) * pl->max_tasks);
   pl->o_recs = take(sizeof(uint4) * 3 * static_cast<size_t>(n));
   pl->total = off;
@@ -926,6 +927,7 @@ void fill_bin_args(const BinPlan& pl, const LevelTab& tab, const float* coords, 
   a->offs = reinterpret_cast<int32_t*>(b + pl.o_offs);
   a->cursor = reinterpret_cast<int32_t*>(b + pl.o_cursor);
   a->n_tasks = reinterpret_cast<int32_t*>(b + pl.o_ntasks);
+  a->scan_state = reinterpret_cast<unsigned long long*>(b + pl.o_scan);
   a->tasks = reinterpret_cast<int2*>(b + pl.o_tasks);
   a->recs = reinterpret_cast<uint4*>(b + pl.o_recs);
   a->zeros = reinterpret_cast<const uint4*>(b + pl.o_zeros);
@@ -1072,15 +1074,13 @@ int launch_grid_bin(const nvp_desc* d, const LevelTab& tab, const float* coords,
   BinArgs a{};
   fill_bin_args(pl, tab, coords, n, binws, &a);
   a.kz = kz;
-  // counters, and (contiguous in the workspace) offs / cursor / n_tasks / the 16 zero bytes
+  // counters, and (contiguous in the workspace) offs / cursor / n_tasks / the 16 zero bytes / the scan's chain state
   NVP_CUDA(cudaMemsetAsync(a.cnt, 0, pl.o_tasks, st));
   const int blocks = static_cast<int>(std::min<int64_t>(8 * device_sms(), (n + 255) / 256));
   ScopedKernelTimer timer(K_BIN, st);
   grid_bin_count_kernel<<<blocks, 256, 0, st>>>(a);
   NVP_LAUNCH_CHECK();
-  const size_t scan_smem = sizeof(int32_t) * 3 * pl.bt.nt;
-  NVP_CUDA(cudaFuncSetAttribute(grid_bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem)));
-  grid_bin_scan_kernel<<<1, 1024, scan_smem, st>>>(a);
+  grid_bin_scan_kernel<<<(3 * pl.bt.nt + 1023) / 1024, 1024, 0, st>>>(a);
   NVP_LAUNCH_CHECK();
   grid_bin_fill_kernel<<<blocks, 256, 0, st>>>(a);
   NVP_LAUNCH_CHECK();

@@ -54,6 +54,7 @@ struct BinArgs {
   int32_t* cursor;         // [3 * nt]     fill cursors
   int2* tasks;             // [max_tasks]  (bucket, first position)
   int32_t* n_tasks;        // [1]
+  unsigned long long* scan_state;   // [1 + 3 * nt / 1024] ticket counter, then one published word per scan CTA (zeroed per call)
   uint4* recs;             // [3 * n]      StagedSample records grouped by bucket (written by the fill kernel)
   // tables
   const float* kf[3];
@@ -105,53 +106,60 @@ __global__ void __launch_bounds__(256) grid_bin_count_kernel(const BinArgs a) {
   }
 }
 
-// One CTA: exclusive prefix sums of the bucket sizes (-> offs, cursor) and of the per-bucket task counts, then the
-// task list itself.  A bucket of c samples becomes ceil(c / chunk) tasks.  The counters are staged in shared memory
-// with coalesced reads; each thread then owns a contiguous run of buckets.
+// Exclusive prefix sums of the bucket sizes (-> offs, cursor) and of the per-bucket task counts, then the task list
+// itself; a bucket of c samples becomes ceil(c / chunk) tasks.  One bucket per thread, 1024 buckets per CTA.  The CTAs
+// chain through `scan_state`: each takes a ticket (its position in scheduling order, so every predecessor is already
+// running), publishes its totals as one 64-bit word (valid bit | samples | tasks) and adds up its predecessors' words.
 __global__ void __launch_bounds__(1024) grid_bin_scan_kernel(const BinArgs a) {
-  extern __shared__ __align__(16) int s_cnt[];   // [3 * nt]
-  __shared__ int s_c[1024], s_t[1024];
-  const int m = 3 * a.bt.nt;
-  {
-    // coalesced 16-byte loads, several in flight per thread (m = 3 * tb^2 is a multiple of 4)
-    const int4* src = reinterpret_cast<const int4*>(a.cnt);
-    int4* dst = reinterpret_cast<int4*>(s_cnt);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < m / 4; i += 1024) dst[i] = __ldg(src + i);
+  __shared__ int s_wc[32], s_wt[32], s_block, s_cpre, s_tpre;
+  const int m = 3 * a.bt.nt, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_block = static_cast<int>(atomicAdd(reinterpret_cast<unsigned int*>(a.scan_state), 1u));
+  __syncthreads();
+  const int b = s_block, i = b * 1024 + static_cast<int>(threadIdx.x);
+  const int c = i < m ? __ldg(a.cnt + i) : 0;
+  const int t = c == 0 ? 0 : (c <= a.bt.chunk ? 1 : (c + a.bt.chunk - 1) / a.bt.chunk);
+  int ic = c, it = t;   // inclusive scans: warp, then across the warps
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int vc = __shfl_up_sync(0xffffffffu, ic, d), vt = __shfl_up_sync(0xffffffffu, it, d);
+    if (lane >= d) { ic += vc; it += vt; }
+  }
+  if (lane == 31) { s_wc[warp] = ic; s_wt[warp] = it; }
+  __syncthreads();
+  if (warp == 0) {
+    int wc = s_wc[lane], wt = s_wt[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int vc = __shfl_up_sync(0xffffffffu, wc, d), vt = __shfl_up_sync(0xffffffffu, wt, d);
+      if (lane >= d) { wc += vc; wt += vt; }
+    }
+    if (lane == 31) {
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long*>(a.scan_state + 1 + b) =
+          (1ull << 63) | (static_cast<unsigned long long>(wc) << 32) | static_cast<unsigned long long>(static_cast<unsigned int>(wt));
+    }
+    s_wc[lane] = wc; s_wt[lane] = wt;   // inclusive over the warps
+    // predecessors' totals
+    int pc = 0, pt = 0;
+    for (int k = lane; k < b; k += 32) {
+      unsigned long long w;
+      do { w = *reinterpret_cast<volatile unsigned long long*>(a.scan_state + 1 + k); } while (!(w >> 63));
+      pc += static_cast<int>((w >> 32) & 0x7fffffffu);
+      pt += static_cast<int>(w & 0xffffffffu);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { pc += __shfl_xor_sync(0xffffffffu, pc, d); pt += __shfl_xor_sync(0xffffffffu, pt, d); }
+    if (lane == 0) { s_cpre = pc; s_tpre = pt; }
   }
   __syncthreads();
-  const int per = ((m + 1023) / 1024) | 1;   // odd run length: the threads' strided walks hit distinct banks
-  const int i0 = min(m, static_cast<int>(threadIdx.x) * per), i1 = min(m, i0 + per);
-  int csum = 0, tsum = 0;
-  for (int i = i0; i < i1; ++i) {
-    const int c = s_cnt[i];
-    csum += c;
-    tsum += c == 0 ? 0 : (c <= a.bt.chunk ? 1 : (c + a.bt.chunk - 1) / a.bt.chunk);
+  const int wbase_c = warp ? s_wc[warp - 1] : 0, wbase_t = warp ? s_wt[warp - 1] : 0;
+  const int off = s_cpre + wbase_c + ic - c;
+  int to = s_tpre + wbase_t + it - t;
+  if (i < m) {
+    a.offs[i] = off; a.cursor[i] = off;
+    for (int bb = 0; bb < c; bb += a.bt.chunk) a.tasks[to++] = make_int2(i, off + bb);
   }
-  s_c[threadIdx.x] = csum; s_t[threadIdx.x] = tsum;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {   // Hillis-Steele inclusive scan
-    const int vc = threadIdx.x >= d ? s_c[threadIdx.x - d] : 0, vt = threadIdx.x >= d ? s_t[threadIdx.x - d] : 0;
-    __syncthreads();
-    s_c[threadIdx.x] += vc; s_t[threadIdx.x] += vt;
-    __syncthreads();
-  }
-  int co = s_c[threadIdx.x] - csum, to = s_t[threadIdx.x] - tsum;
-  for (int i = i0; i < i1; ++i) {
-    const int c = s_cnt[i];
-    s_cnt[i] = co;
-    for (int b = 0; b < c; b += a.bt.chunk) a.tasks[to++] = make_int2(i, co + b);
-    co += c;
-  }
-  __syncthreads();
-  {
-    int4* o4 = reinterpret_cast<int4*>(a.offs);
-    int4* c4 = reinterpret_cast<int4*>(a.cursor);
-    const int4* s4 = reinterpret_cast<const int4*>(s_cnt);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < m / 4; i += 1024) { const int4 o = s4[i]; o4[i] = o; c4[i] = o; }
-  }
-  if (threadIdx.x == 1023) { a.offs[m] = s_c[1023]; a.n_tasks[0] = s_t[1023]; }
+  if (i == m - 1) { a.offs[m] = off + c; a.n_tasks[0] = to; }
 }
 
 __global__ void __launch_bounds__(256) grid_bin_fill_kernel(const BinArgs a) {
