@@ -12,12 +12,13 @@
 // h0, a0, h1, a1 and the five pre-activation gradients (9 tiles per 128 samples instead of 9 + 5 written and 9 read
 // back).  There is no activation stash to re-load and no second weight-ring warm-up per tile.
 //
-// One persistent CTA per SM, one tile in flight, 12 warps:
+// One persistent CTA per SM, one tile in flight, 20 warps (640 threads, 96 registers):
 //   warp 0       TMA producer: weight panel ring (28 panels per tile, in MMA consumption order) + latent tile
 //   warp 1       MMA issuer (one thread): tcgen05.mma M=128, N=128, K=16, accumulators in four 128-column TMEM slots
 //   warps 2-3    reducers: column sums over the tile's samples (dW_last, SIREN bias gradients, layer-0 w/b gradients)
 //                read from the fp16 operand tiles in shared memory, accumulated in fp32 registers across tiles
-//   warps 4-11   epilogue: tcgen05.ld -> fp32 math -> fp16 operand tiles written in the UMMA layout
+//   warps 4-19   epilogue: tcgen05.ld -> fp32 math -> fp16 operand tiles written in the UMMA layout (4 warps per TMEM
+//                lane quarter, 16 columns of a 64-column panel per thread)
 // Phases of a tile (epilogue) and the MMA groups between them:
 //   P0 E(F0) h0,a0 | P1 E(F1) h1,a1 | P2 E(F2) h2,sin2,cos2,a2 -> rgb, loss, drgb | P3 dsp2,dm2 |
 //   P4 E(B1) dsp1,dm1 | P5 E(B0) dsp0,dm0 | P6 dz -> HBM
@@ -70,9 +71,8 @@ struct FusedArgs {
   int n_tiles;
 };
 
-// Per-column constants of the epilogues.  They live in constant memory, not in shared memory: read through the constant
-// cache (LDC, address uniform over the warp) they cost no shared-memory bandwidth, which is what bounds the epilogue
-// phases (the first version read them with LDS.128 and spent a third of the shared-memory pipe on them).
+// Per-column constants of the epilogues, staged once per call by fused_consts_kernel and copied to shared memory by
+// every CTA (or read from constant memory, see NVP_FCONST below - measured slower).
 // The modulator biases are not here: they ride in the GEMMs (see pack_fused_weights).
 struct FusedConsts {
   float bs[3][H];   // SIREN biases, layer 0 pre-multiplied by w0

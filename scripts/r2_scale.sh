@@ -2,7 +2,7 @@
 N=$1; TAG=$2; shift 2
 mkdir -p gpurun_out
 for mode in weak strong; do
-  timeout -k 10 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  timeout -k 10 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29511 + RANDOM % 400)) \
     bench.py --gpus $N --steps 40 --warmup 5 --scaling $mode "$@" > gpurun_out/${TAG}_n${N}_${mode}.json 2> gpurun_out/${TAG}_n${N}_${mode}.err
   echo "$mode rc=$?"
   python - <<PY
