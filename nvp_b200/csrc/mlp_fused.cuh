@@ -818,7 +818,7 @@ int pack_fused_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, cud
   }
   bwd_z(0, 0); fwd_z(0, 0); fwd_z(0, 1); bwd_z(0, 1);
   ScopedKernelTimer timer(K_PACK, st);
-  pack_weights_kernel<<<a.n, 256, 0, st>>>(a);
+  pack_weights_kernel<<<dim3(a.n, 4), 256, 0, st>>>(a);
   NVP_LAUNCH_CHECK();
   return 0;
 }

@@ -68,7 +68,9 @@ struct PackArgs {
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
   const PackPanel& pp = a.p[blockIdx.x];
   uint8_t* dst = a.dst + pp.dst_off;
-  for (int e = threadIdx.x; e < pp.rows * 64; e += blockDim.x) {
+  // blockIdx.y = quarter of the panel: the kernel is latency-bound (dependent load -> 2-byte store per element)
+  const int per = pp.rows * 16;
+  for (int e = blockIdx.y * per + threadIdx.x; e < (blockIdx.y + 1) * per; e += blockDim.x) {
     int r, c;
     if (pp.transpose) { r = e % pp.rows; c = e / pp.rows; } else { r = e >> 6; c = e & 63; }
     float v = 0.0f;
@@ -131,7 +133,7 @@ int pack_forward_weights(const nvp_desc* d, const nvp_params* p, uint8_t* dst, B
   }
   if (b != nullptr) pack_backward_panels(d, p, a, static_cast<uint32_t>(bwd_dst - dst), b);
   ScopedKernelTimer timer(K_PACK, st);
-  pack_weights_kernel<<<a.n, 256, 0, st>>>(a);
+  pack_weights_kernel<<<dim3(a.n, 4), 256, 0, st>>>(a);
   NVP_LAUNCH_CHECK();
   return 0;
 }
