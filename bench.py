@@ -292,7 +292,7 @@ def run_ours(args):
         overlap = GridFirstAllReduce(reduce_view, min(grid_grad_numel(model, flat), reduce_view.numel()))
 
     def step(c, t, g):
-        flat.zero_()
+        trainer.zero_grads()     # (with slab ownership: the replicated gradients + the owned frames only)
         loss_sum.zero_()
         model.fwd_loss_bwd({"all_coords": c, "temporal_steps": t}, g, n_global=n_global, loss_sum=loss_sum,
                            grid_event=overlap.event if overlap else None)

@@ -87,6 +87,17 @@ class FusedTrainer:
     def current_lr(self) -> float:
         return self.optimizers[0].current_lr() if self.fused_optimizer else float(self.scheduler.get_last_lr()[0])
 
+    def zero_grads(self) -> None:
+        """Clear what this rank accumulates into: everything on one GPU; with slab ownership the replicated gradients and
+        the owned frames only (the other frames never receive a gradient on this rank: the routing and the kernels compute
+        the same nearest frame)."""
+        if self.distributed:
+            self.reduce_view.zero_()
+            a, b = self._owned
+            self.flat_grads[a:b].zero_()
+        else:
+            self.flat_grads.zero_()
+
     def local_batch(self, model_input, gt_u8):
         """This rank's share of a GLOBAL batch (identity on one GPU)."""
         if not self.distributed:
