@@ -5,13 +5,16 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1)
 
 A "step" is one pass of the hot path over one batch of N=1,245,184 sampled coordinates (dataio.py:91)
-of a synthetic 1920x1080x600 video: zero the gradient buffer, positional-feature gather, fused
-modulator+SIREN forward, L2 loss, fused backward, weight gradients, grid scatter-add and — with more
-than one GPU — one NCCL all-reduce of the flat gradient buffer.  Prints ONE JSON line (rank 0).
+of a synthetic 1920x1080x600 video: zero the gradient buffer, sample bucketing, positional-feature gather,
+ONE fused kernel for modulator+SIREN forward, L2 loss and backward, grid scatter-add, weight gradients and — with
+more than one GPU — one NCCL all-reduce of the keyframe + MLP gradients (the 3-D grid is owned per rank by t-slab,
+nvp_b200.trainer.FusedTrainer; --scaling strong splits the reference's ONE batch over the GPUs instead of giving each
+its own).  Prints ONE JSON line (rank 0).
 
   value      Mpixels/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
   e2e        same metric through the public module API with HOST (pinned) inputs: H2D copies of
-             coords/tsteps/gt and the D2H read of the loss are inside the timed region
+             coords/tsteps/gt and the D2H read of every step's loss are inside the timed region
+  with_optimizer / unfused_api   the same step + fused AdamW; the reference's model() / loss / backward() sequence
   roofline   the dominant kernel's achieved algorithmic rate vs the measured peak (MEASURED_PEAKS.json),
              timed live with CUDA events on the launch stream; all kernels listed under "kernels"
   cpu_baseline  the oracle (CPU port of the reference arithmetic) timed on this box's host cores on a
