@@ -4,6 +4,8 @@ library reports (nvp_grid_bin_plan) and compared with the oracle's DenseGrid for
 It pins the index logic independently of the CUDA code: bucketing by tile, the per-level window with its aliased
 "virtual" cells (res, j) / (i, res) (unclamped flat index, then modulo the level size - SURVEY A.2), the direct-access
 branch for samples outside their tile's window (coordinates outside [0,1]) and the flush of a window onto the table.
+The scatter-add's bank-interleaved layout with per-lane row ownership is restated lane by lane as well (one lane per
+region address, flush through the table of populated entries).
 The GPU tests check that the kernels implement exactly this (tests/test_gpu_binned.py)."""
 import numpy as np
 import pytest
@@ -123,3 +125,87 @@ def test_interleaved_scatter_layout_is_injective_and_bank_conflict_free():
                 for c1 in (0, 1):
                     banks.append((address(l, aa + rng.integers(0, 2), bb + c1) // 2) % 16)
             assert len(set(banks)) == 16
+
+
+def emulate_interleaved_scatter(u, table, plan, dz):
+    """The scatter-add of grid_binned_kernel<2, true, ..., ILV> for one plane, lane by lane: per task a zeroed region of
+    128-byte rows, lane (level, parity) takes the window row of its own parity, adds into slot (row >> 1) * E + aa of
+    its bank pair, samples outside the window go to the table directly, and the flush walks the table of populated
+    (slot, pair) entries.  Returns the gradient table [cells * 2]."""
+    F, L = 2, table.n_levels
+    tb, ext = plan["tiles_per_axis"], plan["window_extent"]
+    rows = [max((E + 1) // 2 * E for E in ext[:8]), max((E + 1) // 2 * E for E in ext[8:])]
+    grad = np.zeros((int(table.offsets[-1]), F), np.float64)
+    # flush table, built as the kernel builds it: row-major over (region row, bank pair)
+    items = []
+    for row in range(rows[0] + rows[1]):
+        g, slot = (1, row - rows[0]) if row >= rows[0] else (0, row)
+        for p in range(16):
+            l = g * 8 + (p >> 1)
+            if l < L:
+                q, aa = divmod(slot, ext[l])
+                wrow = 2 * q + (p & 1)
+                if wrow < ext[l]:
+                    items.append((row * 32 + p * 2, l, aa, wrow))
+    assert len(items) == sum(E * E for E in ext)
+    b = np.clip((u * np.float32(tb)).astype(np.int32), 0, tb - 1)
+    bucket = b[:, 1] * tb + b[:, 0]
+    for tile in np.unique(bucket):
+        sel = np.nonzero(bucket == tile)[0]
+        ub = np.array([tile % tb, tile // tb], np.float32) / np.float32(tb)
+        region = np.zeros((rows[0] + rows[1]) * 32, np.float64)
+        owner = {}                                                          # region address -> the only lane that may touch it
+        lo = {}
+        for l in range(L):
+            lo[l] = np.floor(O._fmaf(np.full(2, table.scales[l], np.float32), ub, 0.5)).astype(np.int64)
+        for smp in sel:
+            for lane in range(32):
+                l, par = lane >> 1, lane & 1
+                s, res, E, off = table.scales[l], int(table.res[l]), ext[l], int(table.offsets[l])
+                pos = O._fmaf(np.full(2, s, np.float32), u[smp], 0.5)
+                fl = np.floor(pos)
+                w = (pos - fl).astype(np.float32)
+                i0, i1 = int(fl[0]), int(fl[1])
+                aa, bb = i0 - lo[l][0], i1 - lo[l][1]
+                c1 = (bb ^ par) & 1
+                wr = w[1] if c1 else np.float32(1) - w[1]
+                ka, kb = float((np.float32(1) - w[0]) * wr), float(w[0] * wr)
+                d = dz[smp, l * F:(l + 1) * F]
+                amax = np.minimum(E - 2, res - 1 - lo[l])
+                if 0 <= aa <= amax[0] and 0 <= bb <= amax[1]:
+                    wrow = bb + c1
+                    assert (wrow & 1) == par
+                    base = (rows[0] * 32 if lane >= 16 else 0) + ((l & 7) << 2) + (par << 1)
+                    a0 = base + (((wrow >> 1) * E + aa) << 5)
+                    for addr, k in ((a0, ka), (a0 + 32, kb)):
+                        assert owner.setdefault(addr, lane) == lane
+                        region[addr:addr + 2] += k * d
+                else:                                                       # revisited by the direct path after the batch
+                    cells = res * res
+                    for c0, k in ((0, ka), (1, kb)):
+                        grad[off + int(wrap(i0 + c0 + (i1 + c1) * res, cells))] += k * d
+        for addr, l, aa, wrow in items:                                     # flush
+            v = region[addr:addr + 2]
+            res = int(table.res[l])
+            g0, g1 = lo[l][0] + aa, lo[l][1] + wrow
+            if (v != 0).any() and g0 <= res and g1 <= res:
+                grad[int(table.offsets[l]) + int(wrap(g0 + g1 * res, res * res))] += v
+    return grad.reshape(-1)
+
+
+def test_interleaved_scatter_algorithm_equals_the_oracle():
+    L, F = 16, 2
+    d = _lib.NvpDesc(F, L, 16, 1.35, F, 6, 20, 24, 128, 3, 30.0)
+    plan = _lib.grid_bin_plan(d, 4096)
+    table = O.level_table(L, 16, 1.35)
+    rng = np.random.default_rng(7)
+    vals = np.array([0.0, 1.0, 0.5, 63.0 / 64, 1.0 / 1079, 1078.0 / 1079, 127.0 / 128], np.float32)
+    edge = np.stack(np.meshgrid(vals, vals), -1).reshape(-1, 2)
+    clustered = (np.float32(0.37) + rng.random((60, 2)) * np.float32(0.004)).astype(np.float32)   # many samples per window
+    u = np.concatenate([rng.random((120, 2)).astype(np.float32), edge, clustered,
+                        (rng.random((20, 2)) * 1.6 - 0.3).astype(np.float32)])
+    params = torch.zeros(int(table.offsets[-1]) * F, dtype=torch.float64, requires_grad=True)
+    dz = rng.standard_normal((u.shape[0], L * F))
+    (O.dense_grid_forward(params, torch.from_numpy(u), F, table) * torch.from_numpy(dz)).sum().backward()
+    grad = emulate_interleaved_scatter(u, table, plan, dz)
+    assert np.abs(grad - params.grad.numpy()).max() <= 1e-9
