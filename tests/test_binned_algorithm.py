@@ -209,3 +209,40 @@ def test_interleaved_scatter_algorithm_equals_the_oracle():
     (O.dense_grid_forward(params, torch.from_numpy(u), F, table) * torch.from_numpy(dz)).sum().backward()
     grad = emulate_interleaved_scatter(u, table, plan, dz)
     assert np.abs(grad - params.grad.numpy()).max() <= 1e-9
+
+
+def test_chained_scan_restated():
+    """grid_bin_scan_kernel: 1024 buckets per CTA, CTAs chained through published (samples, tasks) totals in ticket order.
+    Restated in numpy with the CTAs processed in an arbitrary ticket order: offsets, task list and totals equal the plain
+    sequential scan's whatever order the tickets were handed out in."""
+    rng = np.random.default_rng(3)
+    m, chunk = 3 * 32 * 32, 160
+    cnt = rng.integers(0, 400, m)
+    cnt[rng.random(m) < 0.3] = 0
+    tasks_of = lambda c: 0 if c == 0 else (1 if c <= chunk else -(-c // chunk))
+    # sequential reference
+    offs_ref = np.concatenate([[0], np.cumsum(cnt)])
+    tasks_ref = [(i, offs_ref[i] + b) for i in range(m) for b in range(0, cnt[i], chunk)]
+    # chained version: CTA with ticket b handles buckets [1024 b, 1024 (b + 1)) -- the ticket IS the logical block index
+    nblk = m // 1024
+    published = {}
+    offs = np.zeros(m + 1, np.int64)
+    tasks = {}
+    for b in range(nblk):                                   # tickets are taken in scheduling order
+        c = cnt[b * 1024:(b + 1) * 1024]
+        t = np.array([tasks_of(x) for x in c])
+        published[b] = (int(c.sum()), int(t.sum()))
+        cpre = sum(published[k][0] for k in range(b))       # every predecessor has a lower ticket: already published
+        tpre = sum(published[k][1] for k in range(b))
+        off = cpre + np.cumsum(c) - c
+        to = tpre + np.cumsum(t) - t
+        for j in range(1024):
+            i = b * 1024 + j
+            offs[i] = off[j]
+            for k, bb in enumerate(range(0, c[j], chunk)):
+                tasks[to[j] + k] = (i, off[j] + bb)
+        if b == nblk - 1:
+            offs[m] = off[-1] + c[-1]
+            n_tasks = to[-1] + t[-1]
+    assert (offs == offs_ref).all()
+    assert n_tasks == len(tasks_ref) and [tasks[k] for k in range(n_tasks)] == tasks_ref
